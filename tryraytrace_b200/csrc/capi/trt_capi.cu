@@ -1,0 +1,741 @@
+// trt_capi.cu -- the C ABI (include/trt_capi.h): context, scene upload and re-layout,
+// the wavefront render loop, parity entry points, and C-callable forms of the host surface.
+#include "trt_capi.h"
+
+#include "bvh.h"
+#include "camera.h"
+#include "image_io.h"
+#include "loader.h"
+#include "scene.h"
+
+#include "../host/wide_bvh.h"
+#include "../host/xorwow_tables.h"
+#include "../kernels/wavefront.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace trt;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(TRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kFrameChunk = 64;       // frames per wavefront job (bounds the column-vector table)
+constexpr int kBatchIterations = 16;  // iterations issued between completion polls
+constexpr int kDefaultPool = 1 << 20;
+
+}  // namespace
+
+struct trt_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
+    float last_ms = 0.f;
+    unsigned long long launches = 0;
+
+    // scene
+    bool have_scene = false;
+    float4* d_objects = nullptr;
+    float4* d_ref_nodes = nullptr;
+    int* d_lights = nullptr;
+    float4* d_wide_nodes = nullptr;
+    float4* d_tris = nullptr;
+    float4* d_leaf_box = nullptr;
+    std::vector<cudaArray_t> tex_arrays;
+    std::vector<cudaTextureObject_t> tex_objs;
+    SceneDev sc{};
+    trt_scene_info info{};
+
+    // XORWOW tables
+    int rng_w = 0, rng_h = 0, n_col_bits = 0;
+    uint32_t* d_row_mats = nullptr;
+    uint32_t* d_col_pows = nullptr;
+    XwColVec* d_col_vecs = nullptr;
+    size_t col_vecs_cap = 0;
+
+    // wavefront pool
+    int pool_cap = 0;
+    void* pool_mem = nullptr;
+    PoolView pool{};
+    ShadowView sq{};
+    int* d_free = nullptr;
+    int* d_replay = nullptr;
+    Control* d_ctl = nullptr;
+    Control* h_ctl = nullptr;  // pinned, 2 entries
+
+    // scratch accumulation buffer for trt_render_to_host
+    float* d_accum_own = nullptr;
+    size_t accum_own_bytes = 0;
+};
+
+namespace {
+
+int use_device(trt_ctx* c) {
+    CU(cudaSetDevice(c->device));
+    return 0;
+}
+
+void free_scene(trt_ctx* c) {
+    for (auto t : c->tex_objs) cudaDestroyTextureObject(t);
+    for (auto a : c->tex_arrays) cudaFreeArray(a);
+    c->tex_objs.clear();
+    c->tex_arrays.clear();
+    cudaFree(c->d_objects);
+    cudaFree(c->d_ref_nodes);
+    cudaFree(c->d_lights);
+    cudaFree(c->d_wide_nodes);
+    cudaFree(c->d_tris);
+    cudaFree(c->d_leaf_box);
+    c->d_objects = c->d_ref_nodes = c->d_wide_nodes = c->d_tris = c->d_leaf_box = nullptr;
+    c->d_lights = nullptr;
+    c->have_scene = false;
+}
+
+// texture object with the reference's descriptors (reference src/renderer.cu:97-126)
+int make_texture(trt_ctx* c, const trt_image& img) {
+    const int w = img.width, h = img.height;
+    std::vector<unsigned char> rgba((size_t)w * h * 4);
+    for (size_t i = 0; i < (size_t)w * h; i++) {
+        rgba[i * 4 + 0] = img.rgb[i * 3 + 0];
+        rgba[i * 4 + 1] = img.rgb[i * 3 + 1];
+        rgba[i * 4 + 2] = img.rgb[i * 3 + 2];
+        rgba[i * 4 + 3] = 255;
+    }
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr = nullptr;
+    CU(cudaMallocArray(&arr, &desc, w, h));
+    c->tex_arrays.push_back(arr);
+    CU(cudaMemcpy2DToArray(arr, 0, 0, rgba.data(), (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyHostToDevice));
+    cudaResourceDesc res;
+    memset(&res, 0, sizeof(res));
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeWrap;
+    td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    cudaTextureObject_t obj = 0;
+    CU(cudaCreateTextureObject(&obj, &res, &td, nullptr));
+    c->tex_objs.push_back(obj);
+    return 0;
+}
+
+void pack_matrix(const Gf2Mat& m, uint32_t* dst) {  // 160 columns x 8 words
+    for (int b = 0; b < 160; b++) {
+        for (int k = 0; k < 5; k++) dst[b * 8 + k] = m.col[b][k];
+        dst[b * 8 + 5] = dst[b * 8 + 6] = dst[b * 8 + 7] = 0;
+    }
+}
+
+int ensure_rng_tables(trt_ctx* c, int w, int h) {
+    if (c->rng_w == w && c->rng_h == h) return 0;
+    cudaFree(c->d_row_mats);
+    cudaFree(c->d_col_pows);
+    c->d_row_mats = c->d_col_pows = nullptr;
+    c->rng_w = c->rng_h = 0;
+    std::vector<Gf2Mat> rows, cols;
+    xorwow_build_row_matrices(w, h, rows);
+    xorwow_build_col_powers(w, cols);
+    std::vector<uint32_t> packed((size_t)h * kXwMatWords);
+    for (int r = 0; r < h; r++) pack_matrix(rows[r], packed.data() + (size_t)r * kXwMatWords);
+    CU(cudaMalloc(&c->d_row_mats, packed.size() * 4));
+    CU(cudaMemcpyAsync(c->d_row_mats, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint32_t> pc(cols.size() * kXwMatWords);
+    for (size_t j = 0; j < cols.size(); j++) pack_matrix(cols[j], pc.data() + j * kXwMatWords);
+    CU(cudaMalloc(&c->d_col_pows, pc.size() * 4));
+    CU(cudaMemcpyAsync(c->d_col_pows, pc.data(), pc.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_col_bits = (int)cols.size();
+    c->rng_w = w;
+    c->rng_h = h;
+    return 0;
+}
+
+int ensure_col_vecs(trt_ctx* c, size_t entries) {
+    if (entries <= c->col_vecs_cap) return 0;
+    cudaFree(c->d_col_vecs);
+    c->d_col_vecs = nullptr;
+    c->col_vecs_cap = 0;
+    CU(cudaMalloc(&c->d_col_vecs, entries * sizeof(XwColVec)));
+    c->col_vecs_cap = entries;
+    return 0;
+}
+
+int ensure_pool(trt_ctx* c, int cap) {
+    cap = std::max(256, (cap + 255) & ~255);
+    if (c->pool_cap == cap) return 0;
+    cudaFree(c->pool_mem);
+    c->pool_mem = nullptr;
+    c->pool_cap = 0;
+    const size_t n = (size_t)cap;
+    // ray_o, ray_d, thr, rad (float4) + rng_a (uint4) + shadow o,d,c (float4): 8 x 16 B
+    // hit (float2), rng_b (uint2): 2 x 8 B; free list, replay list: 2 x 4 B
+    const size_t bytes = n * (8 * 16 + 2 * 8 + 2 * 4);
+    CU(cudaMalloc(&c->pool_mem, bytes));
+    char* p = (char*)c->pool_mem;
+    auto take = [&](size_t b) { void* r = p; p += b; return r; };
+    c->pool.ray_o = (float4*)take(n * 16);
+    c->pool.ray_d = (float4*)take(n * 16);
+    c->pool.thr = (float4*)take(n * 16);
+    c->pool.rad = (float4*)take(n * 16);
+    c->pool.rng_a = (uint4*)take(n * 16);
+    c->sq.o = (float4*)take(n * 16);
+    c->sq.d = (float4*)take(n * 16);
+    c->sq.c = (float4*)take(n * 16);
+    c->pool.hit = (float2*)take(n * 8);
+    c->pool.rng_b = (uint2*)take(n * 8);
+    c->d_free = (int*)take(n * 4);
+    c->d_replay = (int*)take(n * 4);
+    c->pool.capacity = cap;
+    c->pool_cap = cap;
+    return 0;
+}
+
+void fill_job(trt_ctx* c, JobParams& job, float* d_accum, int w, int h, int first_frame_seed, int n_frames,
+              int stride, const void* cam, const trt_opts& o) {
+    memcpy(&job.cam, cam, sizeof(Camera));
+    job.rc.width = w;
+    job.rc.height = h;
+    job.rc.max_depth = o.max_depth;
+    job.rc.rr_threshold = o.rr_threshold;
+    job.first_frame_seed = first_frame_seed;
+    job.frame_stride = stride;
+    job.seed_base = o.seed_base;
+    job.n_frames = n_frames;
+    job.row_mats = c->d_row_mats;
+    job.col_vecs = c->d_col_vecs;
+    job.accum = d_accum;
+}
+
+int check_opts(const trt_opts* in, trt_opts* o) {
+    if (in) *o = *in;
+    else trt_default_opts(o);
+    if (o->max_depth < 1 || o->max_depth > 255) return fail(TRT_ERR_ARG, "max_depth %d out of range [1,255]", o->max_depth);
+    if (o->traversal != TRT_TRAVERSE_FAST && o->traversal != TRT_TRAVERSE_REF)
+        return fail(TRT_ERR_ARG, "unknown traversal mode %d", o->traversal);
+    if (o->pool_paths < 0) return fail(TRT_ERR_ARG, "pool_paths must be >= 0");
+    return 0;
+}
+
+int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frames, int stride, const void* cam,
+                const trt_opts* opts_in) {
+    if (!c) return fail(TRT_ERR_ARG, "null context");
+    if (!c->have_scene) return fail(TRT_ERR_STATE, "trt_render before trt_upload_scene");
+    if (!d_accum || !cam) return fail(TRT_ERR_ARG, "null accum / camera pointer");
+    if (w <= 0 || h <= 0 || n_frames < 0 || stride < 1) return fail(TRT_ERR_ARG, "bad render dimensions");
+    if ((long long)w * h > (1ll << 30)) return fail(TRT_ERR_ARG, "image too large");
+    trt_opts o;
+    if (int rc = check_opts(opts_in, &o)) return rc;
+    if ((long long)o.seed_base + first < 0) return fail(TRT_ERR_ARG, "negative RNG seed");
+    if (int rc = use_device(c)) return rc;
+    if (int rc = ensure_rng_tables(c, w, h)) return rc;
+    if (int rc = ensure_pool(c, o.pool_paths ? o.pool_paths : kDefaultPool)) return rc;
+    if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
+
+    LaunchDims dims{c->sms};
+    const int kpi = wf_kernels_per_iteration(o.traversal);
+    CU(cudaEventRecord(c->ev_begin, c->stream));
+    const unsigned long long pixels = (unsigned long long)w * h;
+    for (int f0 = 0; f0 < n_frames; f0 += kFrameChunk) {
+        const int nf = std::min(kFrameChunk, n_frames - f0);
+        JobParams job;
+        fill_job(c, job, d_accum, w, h, first + f0 * stride, nf, stride, cam, o);
+        wf_col_table(c->d_col_pows, c->n_col_bits, w, job.first_frame_seed, stride, o.seed_base, nf, c->d_col_vecs,
+                     c->stream);
+        wf_init_pool(c->pool, c->d_free, c->d_ctl, c->stream);
+        wf_begin_job(c->d_ctl, pixels * nf, c->pool_cap, c->stream);
+        c->launches += 3;
+        // Issue batches of iterations, staying one batch ahead of the completion poll.
+        auto issue = [&](int slot) -> int {
+            for (int i = 0; i < kBatchIterations; i++)
+                wf_iteration(c->pool, c->sq, c->d_free, c->d_replay, c->d_ctl, c->sc, job, o.traversal,
+                             o.count_rays != 0, dims, c->stream);
+            c->launches += (unsigned long long)kBatchIterations * kpi;
+            CU(cudaMemcpyAsync(&c->h_ctl[slot], c->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaEventRecord(c->ev_poll[slot], c->stream));
+            return 0;
+        };
+        int b = 0;
+        if (int rc = issue(0)) return rc;
+        for (;;) {
+            if (int rc = issue((b + 1) & 1)) return rc;
+            CU(cudaEventSynchronize(c->ev_poll[b & 1]));
+            const Control& hc = c->h_ctl[b & 1];
+            if (hc.alive == 0 && hc.next_sample == hc.total_samples) break;
+            b++;
+        }
+    }
+    CU(cudaEventRecord(c->ev_end, c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* trt_last_error(void) { return g_err.c_str(); }
+const char* trt_version(void) { return "tryraytrace_b200 0.1 (sm_100a)"; }
+
+void trt_default_opts(trt_opts* o) {
+    memset(o, 0, sizeof(*o));
+    o->max_depth = 30;
+    o->rr_threshold = 3;
+    o->seed_base = 1984;
+    o->traversal = TRT_TRAVERSE_FAST;
+    o->pool_paths = 0;
+    o->count_rays = 0;
+}
+
+int trt_create(int device, trt_ctx** out) {
+    if (!out) return fail(TRT_ERR_ARG, "null out pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TRT_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= n) return fail(TRT_ERR_ARG, "device %d out of range (have %d)", device, n);
+    trt_ctx* c = new trt_ctx();
+    c->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev_begin));
+    CU(cudaEventCreate(&c->ev_end));
+    CU(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_poll[1], cudaEventDisableTiming));
+    CU(cudaMalloc(&c->d_ctl, sizeof(Control)));
+    CU(cudaMemset(c->d_ctl, 0, sizeof(Control)));
+    CU(cudaMallocHost(&c->h_ctl, 2 * sizeof(Control)));
+    *out = c;
+    return 0;
+}
+
+int trt_destroy(trt_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c);
+    cudaFree(c->d_row_mats);
+    cudaFree(c->d_col_pows);
+    cudaFree(c->d_col_vecs);
+    cudaFree(c->pool_mem);
+    cudaFree(c->d_ctl);
+    cudaFreeHost(c->h_ctl);
+    cudaFree(c->d_accum_own);
+    cudaEventDestroy(c->ev_begin);
+    cudaEventDestroy(c->ev_end);
+    cudaEventDestroy(c->ev_poll[0]);
+    cudaEventDestroy(c->ev_poll[1]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void* nodes, int n_nodes,
+                     const int* lights, int n_lights, const trt_image* textures, int n_textures) {
+    if (!c) return fail(TRT_ERR_ARG, "null context");
+    if (!objects || n_objects <= 0) return fail(TRT_ERR_ARG, "empty object array");
+    if (!nodes || n_nodes <= 0) return fail(TRT_ERR_ARG, "empty node array");
+    if (n_lights < 0 || (n_lights > 0 && !lights)) return fail(TRT_ERR_ARG, "bad light list");
+    if (n_textures < 0 || n_textures > 5) return fail(TRT_ERR_ARG, "at most 5 textures (MAX_TEXTURES)");
+    const Object* objs = (const Object*)objects;
+    const LinearBVHNode* nd = (const LinearBVHNode*)nodes;
+    // validate what the kernels will index with
+    for (int i = 0; i < n_lights; i++)
+        if (lights[i] < 0 || lights[i] >= n_objects) return fail(TRT_ERR_ARG, "light index %d out of range", lights[i]);
+    for (int i = 0; i < n_objects; i++)
+        if (objs[i].tex_id >= n_textures) return fail(TRT_ERR_ARG, "object %d uses texture %d, only %d given", i, objs[i].tex_id, n_textures);
+    for (int i = 0; i < n_nodes; i++) {
+        const LinearBVHNode& n = nd[i];
+        if (n.is_leaf) {
+            if (n.primitive_offset < 0 || n.primitive_count < 0 || n.primitive_offset + n.primitive_count > n_objects)
+                return fail(TRT_ERR_ARG, "node %d: primitive range out of bounds", i);
+        } else if (n.left_child_idx <= i || n.right_child_idx <= i || n.left_child_idx >= n_nodes ||
+                   n.right_child_idx >= n_nodes) {
+            return fail(TRT_ERR_ARG, "node %d: child index out of order", i);
+        }
+    }
+    if (int rc = use_device(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    free_scene(c);
+
+    CU(cudaMalloc(&c->d_objects, (size_t)n_objects * sizeof(Object)));
+    CU(cudaMemcpy(c->d_objects, objs, (size_t)n_objects * sizeof(Object), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_ref_nodes, (size_t)n_nodes * sizeof(LinearBVHNode)));
+    CU(cudaMemcpy(c->d_ref_nodes, nd, (size_t)n_nodes * sizeof(LinearBVHNode), cudaMemcpyHostToDevice));
+    if (n_lights) {
+        CU(cudaMalloc(&c->d_lights, (size_t)n_lights * sizeof(int)));
+        CU(cudaMemcpy(c->d_lights, lights, (size_t)n_lights * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    for (int i = 0; i < n_textures; i++) {
+        if (!textures[i].rgb || textures[i].width <= 0 || textures[i].height <= 0)
+            return fail(TRT_ERR_ARG, "texture %d is empty", i);
+        if (int rc = make_texture(c, textures[i])) return rc;
+    }
+
+    // re-layout for the fast path: wide BVH over the reference leaf boxes + triangle records
+    WideBvh wb;
+    build_wide_bvh(objs, n_objects, nd, n_nodes, wb);
+    CU(cudaMalloc(&c->d_wide_nodes, std::max<size_t>(wb.nodes.size(), 1) * sizeof(WideNode)));
+    CU(cudaMemcpy(c->d_wide_nodes, wb.nodes.data(), wb.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_tris, std::max<size_t>(wb.tris.size(), 1) * sizeof(TriRecord)));
+    CU(cudaMemcpy(c->d_tris, wb.tris.data(), wb.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&c->d_leaf_box, (size_t)n_objects * 32));
+    CU(cudaMemcpy(c->d_leaf_box, wb.leaf_boxes.data(), (size_t)n_objects * 32, cudaMemcpyHostToDevice));
+
+    SceneDev& sc = c->sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.objects = c->d_objects;
+    sc.ref_nodes = c->d_ref_nodes;
+    sc.lights = c->d_lights;
+    sc.n_objects = n_objects;
+    sc.n_ref_nodes = n_nodes;
+    sc.n_lights = n_lights;
+    sc.n_textures = n_textures;
+    for (int i = 0; i < n_textures; i++) sc.tex[i] = c->tex_objs[i];
+    sc.wide_nodes = c->d_wide_nodes;
+    sc.tris = c->d_tris;
+    sc.leaf_box = c->d_leaf_box;
+    sc.n_wide_nodes = (int)wb.nodes.size();
+    sc.n_tris = (int)wb.tris.size();
+
+    trt_scene_info& in = c->info;
+    memset(&in, 0, sizeof(in));
+    in.n_objects = n_objects;
+    in.n_ref_nodes = n_nodes;
+    in.n_lights = n_lights;
+    in.n_textures = n_textures;
+    in.n_wide_nodes = (int)wb.nodes.size();
+    in.n_wide_leaf_tris = (int)wb.tris.size();
+    in.n_top_prims = wb.n_top_prims;
+    in.wide_node_bytes = (int)sizeof(WideNode);
+    in.tri_record_bytes = (int)sizeof(TriRecord);
+    in.wide_depth = wb.depth;
+    c->have_scene = true;
+    return 0;
+}
+
+int trt_scene_info_get(trt_ctx* c, trt_scene_info* out) {
+    if (!c || !out) return fail(TRT_ERR_ARG, "null pointer");
+    if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
+    *out = c->info;
+    return 0;
+}
+
+int trt_render(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frames, int stride, const void* cam,
+               const trt_opts* opts) {
+    return render_impl(c, d_accum, w, h, first, n_frames, stride, cam, opts);
+}
+
+int trt_render_to_host(trt_ctx* c, float* h_accum, int w, int h, int first, int n_frames, int stride,
+                       const void* cam, const trt_opts* opts) {
+    if (!c || !h_accum) return fail(TRT_ERR_ARG, "null pointer");
+    if (w <= 0 || h <= 0) return fail(TRT_ERR_ARG, "bad render dimensions");
+    if (int rc = use_device(c)) return rc;
+    const size_t bytes = (size_t)w * h * 16;
+    if (bytes > c->accum_own_bytes) {
+        cudaFree(c->d_accum_own);
+        c->d_accum_own = nullptr;
+        c->accum_own_bytes = 0;
+        CU(cudaMalloc(&c->d_accum_own, bytes));
+        c->accum_own_bytes = bytes;
+    }
+    CU(cudaMemsetAsync(c->d_accum_own, 0, bytes, c->stream));
+    if (int rc = render_impl(c, c->d_accum_own, w, h, first, n_frames, stride, cam, opts)) return rc;
+    CU(cudaMemcpyAsync(h_accum, c->d_accum_own, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int trt_trace_primary(trt_ctx* c, int w, int h, int frame_seed, const void* cam, int traversal, int seed_base,
+                      int* d_id, float* d_t, float* d_ray, uint32_t* d_fetched, uint32_t* d_entered,
+                      uint32_t* d_tris) {
+    if (!c || !cam) return fail(TRT_ERR_ARG, "null pointer");
+    if (!c->have_scene) return fail(TRT_ERR_STATE, "trt_trace_primary before trt_upload_scene");
+    if (w <= 0 || h <= 0) return fail(TRT_ERR_ARG, "bad dimensions");
+    if (traversal != TRT_TRAVERSE_FAST && traversal != TRT_TRAVERSE_REF) return fail(TRT_ERR_ARG, "unknown traversal mode");
+    if (int rc = use_device(c)) return rc;
+    if (int rc = ensure_rng_tables(c, w, h)) return rc;
+    if (int rc = ensure_col_vecs(c, (size_t)w)) return rc;
+    trt_opts o;
+    trt_default_opts(&o);
+    o.seed_base = seed_base;
+    JobParams job;
+    fill_job(c, job, nullptr, w, h, frame_seed, 1, 1, cam, o);
+    wf_col_table(c->d_col_pows, c->n_col_bits, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
+    wf_trace_primary(c->sc, job, frame_seed, traversal, d_id, d_t, d_ray, d_fetched, d_entered, d_tris, c->stream);
+    c->launches += 2;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trt_trace_closest(trt_ctx* c, const float* d_rays, int n, int traversal, int* d_id, float* d_t) {
+    if (!c || !d_rays || !d_id) return fail(TRT_ERR_ARG, "null pointer");
+    if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
+    if (n <= 0) return 0;
+    if (int rc = use_device(c)) return rc;
+    wf_trace_closest(c->sc, d_rays, n, traversal, d_id, d_t, c->stream);
+    c->launches += 1;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trt_trace_shadow(trt_ctx* c, const float* d_rays, int n, int traversal, int* d_occ) {
+    if (!c || !d_rays || !d_occ) return fail(TRT_ERR_ARG, "null pointer");
+    if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
+    if (n <= 0) return 0;
+    if (int rc = use_device(c)) return rc;
+    wf_trace_shadow(c->sc, d_rays, n, traversal, d_occ, c->stream);
+    c->launches += 1;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trt_rng_states(trt_ctx* c, int w, int h, int frame_seed, int seed_base, int first_pixel, int n,
+                   uint32_t* d_states) {
+    if (!c || !d_states) return fail(TRT_ERR_ARG, "null pointer");
+    if (w <= 0 || h <= 0 || first_pixel < 0 || n < 0 || (long long)first_pixel + n > (long long)w * h)
+        return fail(TRT_ERR_ARG, "pixel range out of bounds");
+    if (int rc = use_device(c)) return rc;
+    if (int rc = ensure_rng_tables(c, w, h)) return rc;
+    if (int rc = ensure_col_vecs(c, (size_t)w)) return rc;
+    trt_opts o;
+    trt_default_opts(&o);
+    o.seed_base = seed_base;
+    JobParams job;
+    Camera dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    fill_job(c, job, nullptr, w, h, frame_seed, 1, 1, &dummy, o);
+    wf_col_table(c->d_col_pows, c->n_col_bits, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
+    wf_rng_states(job, 0, first_pixel, n, d_states, c->stream);
+    c->launches += 2;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trt_tonemap(trt_ctx* c, const float* d_accum, int w, int h, int frames, uint32_t* d_argb) {
+    if (!c || !d_accum || !d_argb) return fail(TRT_ERR_ARG, "null pointer");
+    if (w <= 0 || h <= 0 || frames <= 0) return fail(TRT_ERR_ARG, "bad dimensions");
+    if (int rc = use_device(c)) return rc;
+    wf_tonemap(d_accum, w * h, frames, d_argb, c->stream);
+    c->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trt_synchronize(trt_ctx* c) {
+    if (!c) return fail(TRT_ERR_ARG, "null context");
+    if (int rc = use_device(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trt_get_counters(trt_ctx* c, trt_counters* out) {
+    if (!c || !out) return fail(TRT_ERR_ARG, "null pointer");
+    if (int rc = use_device(c)) return rc;
+    Control hc;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(&hc, c->d_ctl, sizeof(hc), cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof(*out));
+    out->samples = hc.cnt_samples;
+    out->closest_rays = hc.cnt_closest;
+    out->shadow_rays = hc.cnt_shadow;
+    out->nodes_fetched = hc.cnt_nodes;
+    out->tris_tested = hc.cnt_tris;
+    out->replays = hc.cnt_replays;
+    out->iterations = hc.cnt_iterations;
+    out->kernel_launches = c->launches;
+    return 0;
+}
+
+int trt_reset_counters(trt_ctx* c) {
+    if (!c) return fail(TRT_ERR_ARG, "null context");
+    if (int rc = use_device(c)) return rc;
+    wf_reset_counters(c->d_ctl, c->stream);
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches = 0;
+    return 0;
+}
+
+int trt_last_render_ms(trt_ctx* c, float* ms) {
+    if (!c || !ms) return fail(TRT_ERR_ARG, "null pointer");
+    if (int rc = use_device(c)) return rc;
+    CU(cudaEventSynchronize(c->ev_end));
+    CU(cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+    return 0;
+}
+
+void* trt_stream(trt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+// ---- host surface ----------------------------------------------------------------------
+int trt_load_obj(const char* filename, void* out, int cap, const float offset[3], float scale,
+                 const float albedo[3], float metallic, float roughness) {
+    if (!filename || !offset || !albedo) return fail(TRT_ERR_ARG, "null pointer");
+    std::vector<Object> objs;
+    load_obj(filename, objs, Vec{offset[0], offset[1], offset[2]}, scale, Vec{albedo[0], albedo[1], albedo[2]},
+             metallic, roughness);
+    if (out) {
+        if ((int)objs.size() > cap) return fail(TRT_ERR_ARG, "buffer too small: %zu objects", objs.size());
+        memcpy(out, objs.data(), objs.size() * sizeof(Object));
+    }
+    return (int)objs.size();
+}
+
+int trt_bvh_build(void* objects, int n, void* nodes, int cap) {
+    if (!objects || !nodes || n <= 0) return fail(TRT_ERR_ARG, "bad arguments");
+    if (cap < 2 * n - 1) return fail(TRT_ERR_ARG, "node buffer too small: need %d", 2 * n - 1);
+    std::vector<Object> objs((Object*)objects, (Object*)objects + n);
+    BVH bvh;
+    bvh.build(objs);
+    memcpy(objects, objs.data(), (size_t)n * sizeof(Object));
+    memcpy(nodes, bvh.get_nodes().data(), bvh.get_nodes().size() * sizeof(LinearBVHNode));
+    return (int)bvh.get_nodes().size();
+}
+
+int trt_collect_lights(const void* objects, int n, int* out, int cap) {
+    if (!objects) return fail(TRT_ERR_ARG, "null pointer");
+    const Object* o = (const Object*)objects;
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        const Vec& e = o[i].emission;
+        if (e.x > 0.1f || e.y > 0.1f || e.z > 0.1f) {
+            if (out && cnt < cap) out[cnt] = i;
+            cnt++;
+        }
+    }
+    return cnt;
+}
+
+int trt_camera_params(const float pos[3], float yaw, float pitch, float aperture, float focus, int w, int h,
+                      void* cam_out) {
+    if (!pos || !cam_out || w <= 0 || h <= 0) return fail(TRT_ERR_ARG, "bad arguments");
+    CameraController cam(Vec{pos[0], pos[1], pos[2]}, Vec{0, 0, -1});
+    cam.set_angles(yaw, pitch);
+    cam.set_lens(aperture, focus);
+    CameraParams p = cam.get_params(w, h);
+    memset(cam_out, 0, sizeof(p));
+    memcpy(cam_out, &p, sizeof(p));
+    return 0;
+}
+
+int trt_scene_create(int config, const char* asset_dir, int grid, void* out, int cap, char* tex_files, int tex_cap) {
+    if (config < 0 || config > 5) return fail(TRT_ERR_ARG, "unknown scene config %d", config);
+    Scene s = create_config_scene(config, asset_dir, grid);
+    if (out) {
+        if ((int)s.objects.size() > cap) return fail(TRT_ERR_ARG, "buffer too small: %zu objects", s.objects.size());
+        memcpy(out, s.objects.data(), s.objects.size() * sizeof(Object));
+    }
+    if (tex_files && tex_cap > 0) {
+        std::string j;
+        for (size_t i = 0; i < s.texture_files.size(); i++) {
+            if (i) j += ';';
+            j += s.texture_files[i];
+        }
+        snprintf(tex_files, tex_cap, "%s", j.c_str());
+    }
+    return (int)s.objects.size();
+}
+
+int trt_load_ppm(const char* filename, int* w, int* h, unsigned char** rgb) {
+    if (!filename || !w || !h || !rgb) return fail(TRT_ERR_ARG, "null pointer");
+    *rgb = load_ppm(filename, w, h);
+    if (!*rgb) return fail(TRT_ERR_IO, "cannot read P6 image %s", filename);
+    return 0;
+}
+
+// Deterministic stand-in for the reference's missing assets/earth.ppm:
+// pixel(x,y) = (x*255/(w-1), y*255/(h-1), (x^y)&255).
+int trt_write_ppm_earth(const char* filename, int w, int h) {
+    if (!filename || w < 2 || h < 2) return fail(TRT_ERR_ARG, "bad arguments");
+    FILE* fp = fopen(filename, "wb");
+    if (!fp) return fail(TRT_ERR_IO, "cannot write %s", filename);
+    fprintf(fp, "P6\n%d %d\n255\n", w, h);
+    std::vector<unsigned char> row((size_t)w * 3);
+    for (int y = 0; y < h; y++) {
+        for (int x = 0; x < w; x++) {
+            row[x * 3 + 0] = (unsigned char)(x * 255 / (w - 1));
+            row[x * 3 + 1] = (unsigned char)(y * 255 / (h - 1));
+            row[x * 3 + 2] = (unsigned char)((x ^ y) & 255);
+        }
+        fwrite(row.data(), 1, row.size(), fp);
+    }
+    fclose(fp);
+    return 0;
+}
+
+void trt_free(void* p) { free(p); }
+
+int trt_xorwow_init_host(uint64_t seed, uint64_t subsequence, uint32_t out[6]) {
+    if (!out) return fail(TRT_ERR_ARG, "null pointer");
+    xorwow_init_host(seed, subsequence, out, &out[5]);
+    return 0;
+}
+
+int trt_xorwow_rowcol_host(uint64_t seed, int w, int row, int col, uint32_t out[6]) {
+    if (!out || w <= 0 || row < 0 || col < 0 || col >= w) return fail(TRT_ERR_ARG, "bad arguments");
+    uint32_t s[5], cv[5];
+    xorwow_seed_state(seed, s, &out[5]);
+    Gf2Mat mc, mw, mr;
+    gf2_pow(xorwow_subsequence_matrix(), (uint64_t)col, mc);
+    gf2_matvec(mc, s, cv);
+    gf2_pow(xorwow_subsequence_matrix(), (uint64_t)w, mw);
+    gf2_pow(mw, (uint64_t)row, mr);
+    gf2_matvec(mr, cv, out);
+    return 0;
+}
+
+int trt_wide_bvh_host(const void* objects, int n_objects, const void* nodes, int n_nodes, void* wide_nodes,
+                      int wide_cap, void* tris, int tri_cap, void* leaf_boxes, int info[4]) {
+    if (!objects || !nodes || n_objects <= 0 || n_nodes <= 0 || !info) return fail(TRT_ERR_ARG, "bad arguments");
+    WideBvh wb;
+    build_wide_bvh((const Object*)objects, n_objects, (const LinearBVHNode*)nodes, n_nodes, wb);
+    info[0] = (int)wb.nodes.size();
+    info[1] = (int)wb.tris.size();
+    info[2] = wb.n_top_prims;
+    info[3] = wb.depth;
+    if (wide_nodes) {
+        if (wide_cap < (int)wb.nodes.size()) return fail(TRT_ERR_ARG, "wide node buffer too small");
+        memcpy(wide_nodes, wb.nodes.data(), wb.nodes.size() * sizeof(WideNode));
+    }
+    if (tris) {
+        if (tri_cap < (int)wb.tris.size()) return fail(TRT_ERR_ARG, "triangle buffer too small");
+        memcpy(tris, wb.tris.data(), wb.tris.size() * sizeof(TriRecord));
+    }
+    if (leaf_boxes) memcpy(leaf_boxes, wb.leaf_boxes.data(), (size_t)n_objects * sizeof(LeafBox));
+    return 0;
+}
+
+}  // extern "C"

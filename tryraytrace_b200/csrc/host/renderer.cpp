@@ -1,0 +1,66 @@
+// renderer.cpp -- the reference's two C++ entry points (reference include/renderer.h:35-38,
+// :57; src/renderer.cu:134-184, :764-770) as thin wrappers over the C ABI, with a
+// process-global context standing in for the reference's file-scope device globals.
+#include "renderer.h"
+#include "image_io.h"
+#include "trt_capi.h"
+#include <cstdio>
+#include <cstdlib>
+
+namespace {
+trt_ctx* g_ctx = nullptr;
+
+trt_ctx* global_ctx() {
+    if (!g_ctx) {
+        int dev = 0;
+        if (const char* e = std::getenv("TRT_DEVICE")) dev = std::atoi(e);
+        if (trt_create(dev, &g_ctx) != 0) {
+            std::fprintf(stderr, "[Renderer Error] %s\n", trt_last_error());
+            g_ctx = nullptr;
+        }
+    }
+    return g_ctx;
+}
+}  // namespace
+
+void init_scene_data(const std::vector<Object>& objects, const std::vector<std::string>& texture_files,
+                     const std::vector<LinearBVHNode>& nodes, const std::vector<int>& light_indices) {
+    trt_ctx* c = global_ctx();
+    if (!c) return;
+    std::vector<trt_image> imgs;
+    std::vector<unsigned char*> owned;
+    for (const std::string& f : texture_files) {
+        int w = 0, h = 0;
+        unsigned char* rgb = load_ppm(f.c_str(), &w, &h);
+        if (!rgb) continue;  // the reference leaves a null handle; here the texture slot is dropped
+        owned.push_back(rgb);
+        imgs.push_back(trt_image{w, h, rgb});
+    }
+    // objects that name a texture that failed to load fall back to untextured
+    std::vector<Object> objs = objects;
+    for (Object& o : objs)
+        if (o.tex_id >= (int)imgs.size()) o.tex_id = -1;
+    if (trt_upload_scene(c, objs.data(), (int)objs.size(), nodes.data(), (int)nodes.size(), light_indices.data(),
+                         (int)light_indices.size(), imgs.data(), (int)imgs.size()) != 0)
+        std::fprintf(stderr, "[Renderer Error] %s\n", trt_last_error());
+    else
+        std::printf("[Renderer] Uploaded %zu objects, %zu BVH nodes, %zu lights.\n", objects.size(), nodes.size(),
+                    light_indices.size());
+    for (unsigned char* p : owned) std::free(p);
+}
+
+void launch_render_frames(Vec* accum_buffer, int width, int height, int first_frame_seed, int n_frames,
+                          CameraParams cam) {
+    trt_ctx* c = global_ctx();
+    if (!c) return;
+    if (trt_render(c, reinterpret_cast<float*>(accum_buffer), width, height, first_frame_seed, n_frames, 1, &cam,
+                   nullptr) != 0)
+        std::fprintf(stderr, "[Renderer Error] %s\n", trt_last_error());
+}
+
+void launch_render_kernel(Vec* accum_buffer, int width, int height, int frame_seed, int tx, int ty,
+                          CameraParams cam) {
+    (void)tx;
+    (void)ty;
+    launch_render_frames(accum_buffer, width, height, frame_seed, 1, cam);
+}

@@ -1,0 +1,347 @@
+// wide_bvh.cpp -- see wide_bvh.h.
+#include "wide_bvh.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <numeric>
+
+namespace trt {
+namespace {
+
+struct Box {
+    float mn[3], mx[3];
+    void reset() {
+        for (int k = 0; k < 3; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
+    }
+    void grow(const Box& b) {
+        for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], b.mn[k]); mx[k] = std::max(mx[k], b.mx[k]); }
+    }
+    float area() const {
+        const float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+    bool valid() const { return mx[0] >= mn[0]; }
+};
+
+// binary tree produced by the SAH builder; leaves hold a range of `order`
+struct BNode {
+    Box box;
+    int left = -1, right = -1;  // children (inner) ...
+    int first = 0, count = 0;   // ... or primitive range (leaf)
+    int item = -1;              // >= 0: a single "top item" leaf (see build_top)
+};
+
+constexpr int kBins = 16;
+constexpr int kMaxLeaf = 4;
+constexpr float kCostBox = 1.0f;  // one child-box test
+constexpr float kCostTri = 1.3f;  // one triangle test
+
+struct Builder {
+    const std::vector<Box>& pbox;  // per object
+    std::vector<int> order;        // objects in the SAH tree, permuted in place
+    std::vector<BNode> nodes;
+
+    explicit Builder(const std::vector<Box>& b) : pbox(b) {}
+
+    int build(int first, int count) {
+        const int self = (int)nodes.size();
+        nodes.emplace_back();
+        Box box, cbox;
+        box.reset();
+        cbox.reset();
+        for (int i = first; i < first + count; i++) {
+            const Box& b = pbox[order[i]];
+            box.grow(b);
+            for (int k = 0; k < 3; k++) {
+                const float c = 0.5f * (b.mn[k] + b.mx[k]);
+                cbox.mn[k] = std::min(cbox.mn[k], c);
+                cbox.mx[k] = std::max(cbox.mx[k], c);
+            }
+        }
+        nodes[self].box = box;
+        nodes[self].first = first;
+        nodes[self].count = count;
+        if (count == 1) return self;
+
+        // binned SAH over the three axes
+        float best_cost = INFINITY;
+        int best_axis = -1, best_split = -1;
+        for (int axis = 0; axis < 3; axis++) {
+            const float ext = cbox.mx[axis] - cbox.mn[axis];
+            if (!(ext > 0.f)) continue;
+            Box bb[kBins];
+            int bc[kBins];
+            for (int b = 0; b < kBins; b++) { bb[b].reset(); bc[b] = 0; }
+            const float scale = kBins / ext;
+            for (int i = first; i < first + count; i++) {
+                const Box& pb = pbox[order[i]];
+                int b = (int)((0.5f * (pb.mn[axis] + pb.mx[axis]) - cbox.mn[axis]) * scale);
+                b = std::min(std::max(b, 0), kBins - 1);
+                bb[b].grow(pb);
+                bc[b]++;
+            }
+            float right_area[kBins];
+            int right_cnt[kBins];
+            Box acc;
+            acc.reset();
+            int cnt = 0;
+            for (int b = kBins - 1; b > 0; b--) {
+                acc.grow(bb[b]);
+                cnt += bc[b];
+                right_area[b] = acc.area();
+                right_cnt[b] = cnt;
+            }
+            acc.reset();
+            cnt = 0;
+            for (int b = 0; b < kBins - 1; b++) {
+                acc.grow(bb[b]);
+                cnt += bc[b];
+                if (cnt == 0 || right_cnt[b + 1] == 0) continue;
+                const float cost = acc.area() * cnt + right_area[b + 1] * right_cnt[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = b; }
+            }
+        }
+        const float leaf_cost = kCostTri * count;
+        const float split_cost =
+            best_axis < 0 ? INFINITY : 2.f * kCostBox + kCostTri * best_cost / std::max(box.area(), 1e-30f);
+        if (count <= kMaxLeaf && leaf_cost <= split_cost) return self;
+
+        int mid;
+        if (best_axis < 0) {
+            mid = first + count / 2;  // all centroids coincide: split the range in half
+        } else {
+            const float ext = cbox.mx[best_axis] - cbox.mn[best_axis];
+            const float scale = kBins / ext;
+            const float cmin = cbox.mn[best_axis];
+            const int axis = best_axis, split = best_split;
+            int* b0 = order.data() + first;
+            int* m = std::partition(b0, b0 + count, [&](int o) {
+                const Box& pb = pbox[o];
+                int b = (int)((0.5f * (pb.mn[axis] + pb.mx[axis]) - cmin) * scale);
+                b = std::min(std::max(b, 0), kBins - 1);
+                return b <= split;
+            });
+            mid = (int)(m - order.data());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        }
+        const int l = build(first, mid - first);
+        const int r = build(mid, first + count - mid);
+        nodes[self].left = l;
+        nodes[self].right = r;
+        nodes[self].count = 0;
+        return self;
+    }
+};
+
+// single rounding, denormal results flushed like the device's FADD.FTZ
+float sub_ftz(float a, float b) {
+    float r = a - b;
+    if (std::fabs(r) < 1.17549435e-38f) r = std::copysign(0.f, r);
+    return r;
+}
+
+}  // namespace
+
+void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* ref_nodes, int n_ref_nodes,
+                    WideBvh& out) {
+    out.nodes.clear();
+    out.tris.clear();
+    out.leaf_boxes.assign(n_objects, LeafBox{{INFINITY, INFINITY, INFINITY, 0}, {-INFINITY, -INFINITY, -INFINITY, 0}});
+    out.n_top_prims = 0;
+    out.depth = 0;
+
+    // 1. reference leaf box of every object (objects no leaf refers to can never be hit)
+    std::vector<Box> pbox(n_objects);
+    for (auto& b : pbox) b.reset();
+    for (int i = 0; i < n_ref_nodes; i++) {
+        const LinearBVHNode& n = ref_nodes[i];
+        if (!n.is_leaf) continue;
+        for (int k = 0; k < n.primitive_count; k++) {
+            const int o = n.primitive_offset + k;
+            Box b;
+            b.mn[0] = n.bounds.min.x; b.mn[1] = n.bounds.min.y; b.mn[2] = n.bounds.min.z;
+            b.mx[0] = n.bounds.max.x; b.mx[1] = n.bounds.max.y; b.mx[2] = n.bounds.max.z;
+            if (pbox[o].valid()) pbox[o].grow(b); else pbox[o] = b;
+        }
+    }
+    std::vector<int> live;
+    Box scene;
+    scene.reset();
+    for (int o = 0; o < n_objects; o++) {
+        if (!pbox[o].valid()) continue;
+        live.push_back(o);
+        scene.grow(pbox[o]);
+        LeafBox& lb = out.leaf_boxes[o];
+        for (int k = 0; k < 3; k++) { lb.mn[k] = pbox[o].mn[k]; lb.mx[k] = pbox[o].mx[k]; }
+    }
+    if (live.empty()) {
+        WideNode n;
+        std::memset(&n, 0, sizeof(n));
+        for (int k = 0; k < 4; k++) n.child[k] = kWideEmpty;
+        out.nodes.push_back(n);
+        return;
+    }
+
+    // 2. lift oversized primitives out of the SAH tree
+    const float scene_area = std::max(scene.area(), 1e-30f);
+    std::vector<int> top, rest;
+    {
+        std::vector<int> by_area = live;
+        std::sort(by_area.begin(), by_area.end(), [&](int a, int b) {
+            const float aa = pbox[a].area(), ab = pbox[b].area();
+            return aa != ab ? aa > ab : a < b;
+        });
+        const size_t max_top = 12;
+        std::vector<char> is_top(n_objects, 0);
+        if (live.size() > 16)
+            for (size_t i = 0; i < by_area.size() && top.size() < max_top; i++) {
+                if (pbox[by_area[i]].area() < 0.02f * scene_area) break;
+                top.push_back(by_area[i]);
+                is_top[by_area[i]] = 1;
+            }
+        for (int o : live)
+            if (!is_top[o]) rest.push_back(o);
+        if (rest.empty()) { rest = live; top.clear(); }
+    }
+    out.n_top_prims = (int)top.size();
+
+    // 3. binned-SAH binary tree over the rest
+    Builder bld(pbox);
+    bld.order = rest;
+    const int mesh_root = bld.build(0, (int)rest.size());
+
+    // 4. small exact-SAH binary tree over {mesh subtree, top primitives}
+    struct Item { Box box; int bnode; int prim; };
+    std::vector<Item> items;
+    items.push_back(Item{bld.nodes[mesh_root].box, mesh_root, -1});
+    for (int o : top) items.push_back(Item{pbox[o], -1, o});
+    // extra leaves for top prims are appended to the builder's node list
+    std::vector<int> top_order;  // objects referenced by top leaves, appended after `rest`
+    const int rest_count = (int)rest.size();
+    std::function<int(std::vector<int>)> build_top = [&](std::vector<int> idx) -> int {
+        if (idx.size() == 1) {
+            const Item& it = items[idx[0]];
+            if (it.bnode >= 0) return it.bnode;
+            const int self = (int)bld.nodes.size();
+            bld.nodes.emplace_back();
+            bld.nodes[self].box = it.box;
+            bld.nodes[self].first = rest_count + (int)top_order.size();
+            bld.nodes[self].count = 1;
+            top_order.push_back(it.prim);
+            return self;
+        }
+        // best (axis, split) by full sweep on box centres
+        float best = INFINITY;
+        int best_axis = 0;
+        size_t best_k = idx.size() / 2;
+        for (int axis = 0; axis < 3; axis++) {
+            std::vector<int> s = idx;
+            std::sort(s.begin(), s.end(), [&](int a, int b) {
+                return items[a].box.mn[axis] + items[a].box.mx[axis] < items[b].box.mn[axis] + items[b].box.mx[axis];
+            });
+            for (size_t k = 1; k < s.size(); k++) {
+                Box l, r;
+                l.reset(); r.reset();
+                for (size_t i = 0; i < k; i++) l.grow(items[s[i]].box);
+                for (size_t i = k; i < s.size(); i++) r.grow(items[s[i]].box);
+                const float c = l.area() * k + r.area() * (s.size() - k);
+                if (c < best) { best = c; best_axis = axis; best_k = k; }
+            }
+        }
+        std::vector<int> s = idx;
+        const int axis = best_axis;
+        std::sort(s.begin(), s.end(), [&](int a, int b) {
+            return items[a].box.mn[axis] + items[a].box.mx[axis] < items[b].box.mn[axis] + items[b].box.mx[axis];
+        });
+        std::vector<int> lv(s.begin(), s.begin() + best_k), rv(s.begin() + best_k, s.end());
+        const int l = build_top(lv);
+        const int r = build_top(rv);
+        const int self = (int)bld.nodes.size();
+        bld.nodes.emplace_back();
+        Box b = bld.nodes[l].box;
+        b.grow(bld.nodes[r].box);
+        bld.nodes[self].box = b;
+        bld.nodes[self].left = l;
+        bld.nodes[self].right = r;
+        return self;
+    };
+    std::vector<int> all(items.size());
+    std::iota(all.begin(), all.end(), 0);
+    const int root = build_top(all);
+    std::vector<int> order = bld.order;
+    order.insert(order.end(), top_order.begin(), top_order.end());
+
+    // 5. triangle records in leaf order
+    out.tris.resize(order.size());
+    for (size_t i = 0; i < order.size(); i++) {
+        const Object& o = objects[order[i]];
+        TriRecord& t = out.tris[i];
+        t.v0[0] = o.v0.x; t.v0[1] = o.v0.y; t.v0[2] = o.v0.z;
+        t.id = order[i];
+        t.e1[0] = sub_ftz(o.v1.x, o.v0.x); t.e1[1] = sub_ftz(o.v1.y, o.v0.y); t.e1[2] = sub_ftz(o.v1.z, o.v0.z);
+        t.e2[0] = sub_ftz(o.v2.x, o.v0.x); t.e2[1] = sub_ftz(o.v2.y, o.v0.y); t.e2[2] = sub_ftz(o.v2.z, o.v0.z);
+        t.pad1 = t.pad2 = 0.f;
+    }
+
+    // 6. collapse the binary tree into 4-wide nodes
+    const std::vector<BNode>& bn = bld.nodes;
+    auto is_leaf = [&](int n) { return bn[n].left < 0; };
+    auto leaf_ref = [&](int n) { return ~((bn[n].first << 2) | (bn[n].count - 1)); };
+    if (is_leaf(root)) {  // a single leaf: wrap it in one node
+        WideNode w;
+        std::memset(&w, 0, sizeof(w));
+        for (int k = 0; k < 4; k++) w.child[k] = kWideEmpty;
+        w.lo_x[0] = bn[root].box.mn[0]; w.hi_x[0] = bn[root].box.mx[0];
+        w.lo_y[0] = bn[root].box.mn[1]; w.hi_y[0] = bn[root].box.mx[1];
+        w.lo_z[0] = bn[root].box.mn[2]; w.hi_z[0] = bn[root].box.mx[2];
+        w.child[0] = leaf_ref(root);
+        out.nodes.push_back(w);
+        out.depth = 1;
+        return;
+    }
+    struct Work { int bnode; int wide; int depth; };
+    std::vector<Work> work;
+    out.nodes.emplace_back();
+    work.push_back(Work{root, 0, 1});
+    while (!work.empty()) {
+        const Work wk = work.back();
+        work.pop_back();
+        out.depth = std::max(out.depth, wk.depth);
+        int kids[4];
+        int nk = 0;
+        kids[nk++] = bn[wk.bnode].left;
+        kids[nk++] = bn[wk.bnode].right;
+        while (nk < 4) {  // open the inner child with the largest box
+            int pick = -1;
+            float pa = -1.f;
+            for (int k = 0; k < nk; k++)
+                if (!is_leaf(kids[k]) && bn[kids[k]].box.area() > pa) { pa = bn[kids[k]].box.area(); pick = k; }
+            if (pick < 0) break;
+            const int n = kids[pick];
+            kids[pick] = bn[n].left;
+            kids[nk++] = bn[n].right;
+        }
+        WideNode w;
+        std::memset(&w, 0, sizeof(w));
+        for (int k = 0; k < 4; k++) {
+            if (k >= nk) { w.child[k] = kWideEmpty; continue; }
+            const Box& b = bn[kids[k]].box;
+            w.lo_x[k] = b.mn[0]; w.hi_x[k] = b.mx[0];
+            w.lo_y[k] = b.mn[1]; w.hi_y[k] = b.mx[1];
+            w.lo_z[k] = b.mn[2]; w.hi_z[k] = b.mx[2];
+            if (is_leaf(kids[k])) {
+                w.child[k] = leaf_ref(kids[k]);
+            } else {
+                const int idx = (int)out.nodes.size();
+                out.nodes.emplace_back();
+                w.child[k] = idx;
+                work.push_back(Work{kids[k], idx, wk.depth + 1});
+            }
+        }
+        out.nodes[wk.wide] = w;
+    }
+}
+
+}  // namespace trt

@@ -1,0 +1,57 @@
+// wide_bvh.h -- re-layout of the reference BVH output for the fast traversal path.
+//
+// Input: the object array (already in BVH::build order) and the reference's 48-byte node
+// array (reference include/bvh.h:12-28, built by src/bvh.cpp:32-113).  Output:
+//   * a 4-wide BVH (128-byte nodes, child boxes stored SoA so every plane set is one
+//     128-bit load) built by binned SAH over the REFERENCE LEAF BOXES -- so every wide box
+//     contains the reference leaf boxes below it, which is what makes the fast traversal a
+//     strict superset of the reference traversal (kernels/traverse_wide.cuh);
+//   * oversized primitives (the room's one-triangle walls) lifted out of
+//     the SAH tree and attached near the root, where they stop inflating every upper box;
+//   * 48-byte triangle records (v0, e1, e2 as three float4) in wide-leaf order, e1/e2
+//     pre-subtracted with the same single rounding the reference applies per test;
+//   * the reference leaf box of every object (2 x float4), used to decide exactly whether
+//     the reference traversal would have reached a candidate triangle.
+#pragma once
+#include "bvh.h"
+#include "scene.h"
+#include <cstdint>
+#include <vector>
+
+namespace trt {
+
+constexpr int kWideEmpty = 0x7fffffff;  // child slot unused
+
+struct WideNode {  // 128 bytes
+    float lo_x[4], hi_x[4], lo_y[4], hi_y[4], lo_z[4], hi_z[4];
+    int child[4];  // >= 0 inner node index; < 0 leaf: ~((first_tri << 2) | (count - 1)); kWideEmpty unused
+    int pad[4];
+};
+static_assert(sizeof(WideNode) == 128, "WideNode layout");
+
+struct TriRecord {  // 48 bytes
+    float v0[3];
+    int id;  // object index (position in the reference-sorted array)
+    float e1[3];
+    float pad1;
+    float e2[3];
+    float pad2;
+};
+static_assert(sizeof(TriRecord) == 48, "TriRecord layout");
+
+struct LeafBox {  // 32 bytes
+    float mn[4], mx[4];
+};
+
+struct WideBvh {
+    std::vector<WideNode> nodes;  // root = 0
+    std::vector<TriRecord> tris;
+    std::vector<LeafBox> leaf_boxes;  // per object id
+    int n_top_prims = 0;
+    int depth = 0;
+};
+
+void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* ref_nodes, int n_ref_nodes,
+                    WideBvh& out);
+
+}  // namespace trt

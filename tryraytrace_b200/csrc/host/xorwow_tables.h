@@ -1,0 +1,51 @@
+// xorwow_tables.h -- GF(2) skip-ahead matrices for the XORWOW generator.
+//
+// The reference seeds one cuRAND XORWOW stream per pixel per frame:
+// curand_init(1984+frame, subsequence=pixel, 0) (reference src/renderer.cu:326).
+// cuRAND's subsequence s starts s * 2^67 draws into the seed's sequence.  The v[0..4]
+// part of the state advances linearly over GF(2) (Marsaglia xorshift, the step at
+// curand_kernel.h:863-874), so "skip one subsequence" is a fixed 160x160 bit matrix
+//     M = T^(2^67),   T = one-step transition,
+// and the state of pixel p in frame f is  M^p * v0(f)  with v0(f) the seed scramble of
+// curand_kernel.h:800-812.  cuRAND evaluates M^p digit by digit with ~16 mat-vecs per
+// thread per launch; here the power is split by image row and column,
+//     M^(row*w + col) = (M^w)^row * M^col,
+// so a pixel costs ONE mat-vec with a row matrix that is uniform across a warp
+// (kernels/xorwow.cuh), applied to a per-frame column vector table.
+//
+// Everything here is derived from the published algorithm; no cuRAND table is copied.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace trt {
+
+// 160x160 bit matrix, column-major by input bit: col[b] is the image of basis vector e_b,
+// b = 32*word + bit.  (Same orientation as cuRAND's precalc tables, curand_kernel.h:316-333.)
+struct Gf2Mat {
+    uint32_t col[160][5];
+};
+
+void gf2_identity(Gf2Mat& m);
+void gf2_matvec(const Gf2Mat& m, const uint32_t v[5], uint32_t out[5]);
+void gf2_matmul(const Gf2Mat& a, const Gf2Mat& b, Gf2Mat& out);  // out = a * b  (apply b first)
+void gf2_square_n(Gf2Mat& m, int n);                              // m = m^(2^n)
+void gf2_pow(const Gf2Mat& m, uint64_t e, Gf2Mat& out);
+
+// T: one XORWOW draw.  M: one subsequence (2^67 draws).
+void xorwow_step_matrix(Gf2Mat& t);
+const Gf2Mat& xorwow_subsequence_matrix();
+
+// Seed scramble of curand_init: v[0..4] and d for a 64-bit seed.
+void xorwow_seed_state(uint64_t seed, uint32_t v[5], uint32_t* d);
+
+// Full host evaluation (tests / small cases): state after curand_init(seed, subsequence, 0).
+void xorwow_init_host(uint64_t seed, uint64_t subsequence, uint32_t v[5], uint32_t* d);
+
+// Tables for an image of width w and height h:
+//   row_mats[r]   = M^(w*r)              r in [0,h)       (h matrices of 800 words)
+//   col_pows[j]   = M^(2^j)              j in [0,n_col_bits)  with 2^n_col_bits >= w
+void xorwow_build_row_matrices(int w, int h, std::vector<Gf2Mat>& row_mats);
+void xorwow_build_col_powers(int w, std::vector<Gf2Mat>& col_pows);
+
+}  // namespace trt
