@@ -146,8 +146,11 @@ int trt_reset_counters(trt_ctx* ctx);
 /* Milliseconds the last trt_render spent between its first and last kernel,
  * measured with CUDA events on the context's stream (valid after synchronise). */
 int trt_last_render_ms(trt_ctx* ctx, float* ms);
-/* The CUDA stream (cudaStream_t) the context launches on. */
+/* The CUDA stream (cudaStream_t) the context launches on, and a way to make it launch on a
+ * caller-owned stream instead (NULL restores the context's own stream).  The reference
+ * launches on the legacy default stream (src/renderer.cu:769). */
 void* trt_stream(trt_ctx* ctx);
+int trt_set_stream(trt_ctx* ctx, void* cuda_stream);
 
 /* Host surface, C-callable forms of the reference's C++ entry points. */
 /* load_obj (include/loader.h:12-13, src/loader.cpp:22-103): returns the number of

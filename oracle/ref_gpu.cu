@@ -204,6 +204,7 @@ int ref_init_scene(const void* objects, int n, const void* nodes, int n_nodes, c
     g_lights.assign(lights, lights + n_lights);
     g_tex = split(tex_files);
     init_scene_data(g_objects, g_tex, g_nodes, g_lights);
+    if (g_lights.empty()) d_light_indices = nullptr;  // see ref_first_hit_ids
     cudaDeviceSynchronize();
     return cuda_ok();
 }
@@ -254,6 +255,9 @@ int ref_first_hit_ids(int w, int h, int frame_seed, const void* cam, int* h_ids)
     std::vector<int> no_lights;
     std::vector<std::string> no_tex;
     init_scene_data(coded, no_tex, g_nodes, no_lights);
+    // The reference frees d_light_indices but keeps the stale pointer when the new list is empty
+    // (src/renderer.cu:173-183); clear it so the restoring call below does not free it twice.
+    d_light_indices = nullptr;
     const size_t n = (size_t)w * h;
     Vec* d_acc = nullptr;
     cudaMalloc(&d_acc, n * sizeof(Vec));
@@ -276,6 +280,7 @@ int ref_first_hit_ids(int w, int h, int frame_seed, const void* cam, int* h_ids)
     }
     // restore the real scene
     init_scene_data(g_objects, g_tex, g_nodes, g_lights);
+    if (g_lights.empty()) d_light_indices = nullptr;
     cudaDeviceSynchronize();
     int rc = cuda_ok();
     return rc ? rc : bad;

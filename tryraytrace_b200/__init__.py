@@ -349,3 +349,7 @@ class Context:
 
     def stream(self):
         return lib().trt_stream(self._h)
+
+    def set_stream(self, cuda_stream):
+        """Launch on a caller-owned stream (an int cudaStream_t, e.g. torch's current stream)."""
+        _check(lib().trt_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))

@@ -46,13 +46,15 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kFrameChunk = 64;       // frames per wavefront job (bounds the column-vector table)
 constexpr int kBatchIterations = 16;  // iterations issued between completion polls
 constexpr int kDefaultPool = 1 << 20;
+constexpr int kWideStackEntries = 48;  // kernels/traverse_wide.cuh kNodeStack
 
 }  // namespace
 
 struct trt_ctx {
     int device = 0;
     int sms = 148;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream in use
+    cudaStream_t own_stream = nullptr;  // created by trt_create
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
     float last_ms = 0.f;
     unsigned long long launches = 0;
@@ -259,7 +261,8 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_pool(c, o.pool_paths ? o.pool_paths : kDefaultPool)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
-    LaunchDims dims{c->sms};
+    LaunchDims dims{c->sms, 10};
+    if (const char* e = getenv("TRT_FAST_BLOCKS")) dims.fast_blocks_per_sm = std::max(1, atoi(e));
     const int kpi = wf_kernels_per_iteration(o.traversal);
     CU(cudaEventRecord(c->ev_begin, c->stream));
     const unsigned long long pixels = (unsigned long long)w * h;
@@ -282,14 +285,23 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
             CU(cudaEventRecord(c->ev_poll[slot], c->stream));
             return 0;
         };
-        int b = 0;
+        // every iteration advances each live path by one vertex, so the job needs at most
+        // (samples / pool + 1) * (max_depth + 2) iterations; anything beyond that is a bug
+        const unsigned long long max_batches =
+            ((pixels * nf) / (unsigned long long)c->pool_cap + 2) * (unsigned long long)(o.max_depth + 2) /
+                kBatchIterations + 8;
+        unsigned long long b = 0;
         if (int rc = issue(0)) return rc;
         for (;;) {
-            if (int rc = issue((b + 1) & 1)) return rc;
+            if (int rc = issue((int)((b + 1) & 1))) return rc;
             CU(cudaEventSynchronize(c->ev_poll[b & 1]));
             const Control& hc = c->h_ctl[b & 1];
             if (hc.alive == 0 && hc.next_sample == hc.total_samples) break;
-            b++;
+            if (++b > max_batches) {
+                cudaStreamSynchronize(c->stream);
+                return fail(TRT_ERR_STATE, "wavefront did not drain after %llu batches (alive=%d, next=%llu of %llu)",
+                            b, hc.alive, hc.next_sample, hc.total_samples);
+            }
         }
     }
     CU(cudaEventRecord(c->ev_end, c->stream));
@@ -326,7 +338,8 @@ int trt_create(int device, trt_ctx** out) {
     c->device = device;
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev_begin));
     CU(cudaEventCreate(&c->ev_end));
     CU(cudaEventCreateWithFlags(&c->ev_poll[0], cudaEventDisableTiming));
@@ -354,7 +367,7 @@ int trt_destroy(trt_ctx* c) {
     cudaEventDestroy(c->ev_end);
     cudaEventDestroy(c->ev_poll[0]);
     cudaEventDestroy(c->ev_poll[1]);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
 }
@@ -404,6 +417,8 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
     // re-layout for the fast path: wide BVH over the reference leaf boxes + triangle records
     WideBvh wb;
     build_wide_bvh(objs, n_objects, nd, n_nodes, wb);
+    if (3 * wb.depth + 1 > kWideStackEntries)
+        return fail(TRT_ERR_ARG, "wide BVH depth %d exceeds the traversal stack", wb.depth);
     CU(cudaMalloc(&c->d_wide_nodes, std::max<size_t>(wb.nodes.size(), 1) * sizeof(WideNode)));
     CU(cudaMemcpy(c->d_wide_nodes, wb.nodes.data(), wb.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_tris, std::max<size_t>(wb.tris.size(), 1) * sizeof(TriRecord)));
@@ -599,6 +614,14 @@ int trt_last_render_ms(trt_ctx* c, float* ms) {
 }
 
 void* trt_stream(trt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int trt_set_stream(trt_ctx* c, void* cuda_stream) {
+    if (!c) return fail(TRT_ERR_ARG, "null context");
+    if (int rc = use_device(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return 0;
+}
 
 // ---- host surface ----------------------------------------------------------------------
 int trt_load_obj(const char* filename, void* out, int cap, const float offset[3], float scale,

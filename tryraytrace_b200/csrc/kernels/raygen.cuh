@@ -25,8 +25,11 @@ TRT_DEV Ray primary_ray(const Camera& cam, int x, int y, int w, int h, Xorwow& r
     const float u1 = xw_uniform(rng);
     const float dx = tent(p_add(u0, u0));
     const float dy = tent(p_add(u1, u1));
-    const float sx = p_add(p_div(p_add(p_add((float)x, 0.5f), dx), (float)w), -0.5f);
-    const float sy = p_add(p_div(p_add(p_add((float)y, 0.5f), dy), (float)h), -0.5f);
+    // (x + .5 + dx) / w - .5: ptxas expands the approximate division into rcp * numerator and
+    // contracts that multiply with the following subtraction (FFMA num, rcp(w), -0.5 in the
+    // reference SASS), so the quotient is never rounded on its own
+    const float sx = p_fma(p_add(p_add((float)x, 0.5f), dx), p_rcp((float)w), -0.5f);
+    const float sy = p_fma(p_add(p_add((float)y, 0.5f), dy), p_rcp((float)h), -0.5f);
     F3 dir = f3(p_add(cam.dir.x, p_fma(cam.cx.x, sx, p_mul(cam.cy.x, sy))),
                 p_add(cam.dir.y, p_fma(cam.cx.y, sx, p_mul(cam.cy.y, sy))),
                 p_add(cam.dir.z, p_fma(cam.cx.z, sx, p_mul(cam.cy.z, sy))));

@@ -300,6 +300,142 @@ __global__ void __launch_bounds__(kBlock) k_shadow(PoolView pool, ShadowView sq,
     }
 }
 
+
+// ---- persistent fast-path kernels: while-while traversal with dynamic ray fetch -------------
+// One warp holds 32 rays.  Rounds (traverse_wide.cuh) keep the lanes converged; a lane whose
+// ray has finished writes its result and goes idle; when a quarter of the warp is idle the
+// idle lanes grab the next slots from a global cursor with one warp-aggregated atomic
+// (__ballot_sync + __popc) and continue -- so a long ray never holds 31 finished lanes hostage.
+constexpr int kFastBlock = 128;
+constexpr int kRefillBelow = 25;  // refill when fewer than this many lanes hold a ray
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kFastBlock) k_extend_fast(PoolView pool, SceneDev sc, Control* ctl) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    ClosestState st;
+    st.nsp = 0;
+    st.tsp = 0;
+    WideCounts wc = {0, 0};
+    bool has = false;
+    bool drained = false;  // warp-uniform: the cursor ran past the pool
+    int slot = -1;
+    unsigned replays = 0;
+    for (;;) {
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!drained && __popc(act) < kRefillBelow) {
+            const unsigned idle = ~act;
+            const int n = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->cursor_extend, n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!has) {
+                const int my = base + __popc(idle & lt_mask);
+                if (my < pool.capacity) {
+                    const float4 d4 = pool.ray_d[my];
+                    if ((f2i(d4.w) & 0xff) == SLOT_ACTIVE) {
+                        const float4 o4 = pool.ray_o[my];
+                        Ray r;
+                        r.o = f3(o4.x, o4.y, o4.z);
+                        r.d = f3(d4.x, d4.y, d4.z);
+                        closest_begin(st, r);
+                        has = true;
+                        slot = my;
+                    }
+                }
+            }
+            drained = base + n >= pool.capacity;
+            act = __ballot_sync(0xffffffffu, has);
+        }
+        if (act == 0) {
+            if (drained) break;
+            continue;
+        }
+        if (has) {
+            closest_round<COUNT>(sc, st, &wc);
+            if (closest_done(st)) {
+                float t = st.d_min;
+                int id = st.id;
+                if (st.amb) {  // rare: order-dependent reach, re-run in reference order
+                    Ray r;
+                    r.o = st.o;
+                    r.d = st.d;
+                    VisitCounts vc = {0, 0, 0};
+                    id = ref_closest<false>(sc, r, &t, &vc);
+                    replays++;
+                }
+                pool.hit[slot] = make_float2(t, i2f(id));
+                has = false;
+            }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&ctl->cnt_nodes, (unsigned long long)wc.nodes);
+        atomicAdd(&ctl->cnt_tris, (unsigned long long)wc.tris);
+    }
+    if (replays) atomicAdd(&ctl->cnt_replays, (unsigned long long)replays);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kFastBlock) k_shadow_fast(PoolView pool, ShadowView sq, SceneDev sc, Control* ctl) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int n_rays = ctl->n_shadow;
+    ShadowState st;
+    st.nsp = 0;
+    st.tsp = 0;
+    st.occluded = false;
+    WideCounts wc = {0, 0};
+    bool has = false;
+    bool drained = false;
+    int entry = -1;
+    for (;;) {
+        unsigned act = __ballot_sync(0xffffffffu, has);
+        if (!drained && __popc(act) < kRefillBelow) {
+            const unsigned idle = ~act;
+            const int n = __popc(idle);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->cursor_shadow, n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!has) {
+                const int my = base + __popc(idle & lt_mask);
+                if (my < n_rays) {
+                    const float4 o4 = sq.o[my], d4 = sq.d[my];
+                    Ray r;
+                    r.o = f3(o4.x, o4.y, o4.z);
+                    r.d = f3(d4.x, d4.y, d4.z);
+                    shadow_begin(st, r, o4.w);
+                    has = true;
+                    entry = my;
+                }
+            }
+            drained = base + n >= n_rays;
+            act = __ballot_sync(0xffffffffu, has);
+        }
+        if (act == 0) {
+            if (drained) break;
+            continue;
+        }
+        if (has) {
+            shadow_round<COUNT>(sc, st, &wc);
+            if (shadow_done(st)) {
+                if (!st.occluded) {
+                    const int slot = f2i(sq.d[entry].w);
+                    const float4 c = sq.c[entry];
+                    float4 rad = pool.rad[slot];  // one shadow ray per slot per iteration: no race
+                    rad.x += c.x; rad.y += c.y; rad.z += c.z;
+                    pool.rad[slot] = rad;
+                }
+                has = false;
+            }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&ctl->cnt_nodes, (unsigned long long)wc.nodes);
+        atomicAdd(&ctl->cnt_tris, (unsigned long long)wc.tris);
+    }
+}
+
 // ---- parity / test entry points -------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_trace_primary(SceneDev sc, JobParams job, int* out_id, float* out_t,
@@ -443,9 +579,17 @@ static void iteration_impl(const PoolView& pool, const ShadowView& sq, int* free
     const int persistent = dims.sms * 8;
     k_prepare<<<1, 32, 0, s>>>(ctl);
     k_regen<<<persistent < full ? persistent : full, kBlock, 0, s>>>(pool, free_list, ctl, job);
-    k_extend<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl, replay_list);
-    k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
-    k_shadow<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sq, sc, ctl);
+    if (MODE == TRT_TRAVERSE_FAST) {
+        // persistent grids: enough CTAs to fill every SM, each warp pulls rays until the queue is dry
+        const int fast_grid = dims.sms * dims.fast_blocks_per_sm;
+        k_extend_fast<COUNT><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
+        k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+        k_shadow_fast<COUNT><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
+    } else {
+        k_extend<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl, replay_list);
+        k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+        k_shadow<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sq, sc, ctl);
+    }
 }
 
 void wf_iteration(const PoolView& pool, const ShadowView& sq, int* free_list, int* replay_list, Control* ctl,

@@ -65,6 +65,7 @@ struct JobParams {
 
 struct LaunchDims {
     int sms;
+    int fast_blocks_per_sm;  // resident CTAs per SM of the persistent traversal kernels
 };
 
 // ---- launchers (wavefront.cu) --------------------------------------------------------
