@@ -261,7 +261,9 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_pool(c, o.pool_paths ? o.pool_paths : kDefaultPool)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
-    LaunchDims dims{c->sms, 10};
+    LaunchDims dims{c->sms, 8, 8};
+    if (const char* e = getenv("TRT_FAST_VARIANT")) dims.fast_variant = atoi(e);
+    dims.fast_blocks_per_sm = dims.fast_variant == 4 ? 4 : (dims.fast_variant == 6 ? 6 : 8);
     if (const char* e = getenv("TRT_FAST_BLOCKS")) dims.fast_blocks_per_sm = std::max(1, atoi(e));
     const int kpi = wf_kernels_per_iteration(o.traversal);
     CU(cudaEventRecord(c->ev_begin, c->stream));

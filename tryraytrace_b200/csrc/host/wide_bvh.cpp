@@ -135,6 +135,18 @@ struct Builder {
     }
 };
 
+// An unused child slot gets an inverted infinite box (lo = +inf, hi = -inf): whichever plane the
+// ray's direction sign selects as "near", the slab interval comes out empty, so the traversal
+// kernels need no special case for it.
+void clear_node(WideNode& w) {
+    std::memset(&w, 0, sizeof(w));
+    for (int k = 0; k < 4; k++) {
+        w.lo_x[k] = w.lo_y[k] = w.lo_z[k] = INFINITY;
+        w.hi_x[k] = w.hi_y[k] = w.hi_z[k] = -INFINITY;
+        w.child[k] = kWideEmpty;
+    }
+}
+
 // single rounding, denormal results flushed like the device's FADD.FTZ
 float sub_ftz(float a, float b) {
     float r = a - b;
@@ -178,8 +190,7 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
     }
     if (live.empty()) {
         WideNode n;
-        std::memset(&n, 0, sizeof(n));
-        for (int k = 0; k < 4; k++) n.child[k] = kWideEmpty;
+        clear_node(n);
         out.nodes.push_back(n);
         return;
     }
@@ -291,8 +302,7 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
     auto leaf_ref = [&](int n) { return ~((bn[n].first << 2) | (bn[n].count - 1)); };
     if (is_leaf(root)) {  // a single leaf: wrap it in one node
         WideNode w;
-        std::memset(&w, 0, sizeof(w));
-        for (int k = 0; k < 4; k++) w.child[k] = kWideEmpty;
+        clear_node(w);
         w.lo_x[0] = bn[root].box.mn[0]; w.hi_x[0] = bn[root].box.mx[0];
         w.lo_y[0] = bn[root].box.mn[1]; w.hi_y[0] = bn[root].box.mx[1];
         w.lo_z[0] = bn[root].box.mn[2]; w.hi_z[0] = bn[root].box.mx[2];
@@ -324,9 +334,9 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
             kids[nk++] = bn[n].right;
         }
         WideNode w;
-        std::memset(&w, 0, sizeof(w));
+        clear_node(w);
         for (int k = 0; k < 4; k++) {
-            if (k >= nk) { w.child[k] = kWideEmpty; continue; }
+            if (k >= nk) continue;
             const Box& b = bn[kids[k]].box;
             w.lo_x[k] = b.mn[0]; w.hi_x[k] = b.mx[0];
             w.lo_y[k] = b.mn[1]; w.hi_y[k] = b.mx[1];

@@ -309,13 +309,15 @@ __global__ void __launch_bounds__(kBlock) k_shadow(PoolView pool, ShadowView sq,
 constexpr int kFastBlock = 128;
 constexpr int kRefillBelow = 25;  // refill when fewer than this many lanes hold a ray
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kFastBlock) k_extend_fast(PoolView pool, SceneDev sc, Control* ctl) {
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_extend_fast(PoolView pool, SceneDev sc, Control* ctl) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     ClosestState st;
+    ClosestStack stack;
     st.nsp = 0;
     st.tsp = 0;
+    st.cur = kWideEmptyRef;
     WideCounts wc = {0, 0};
     bool has = false;
     bool drained = false;  // warp-uniform: the cursor ran past the pool
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kFastBlock) k_extend_fast(PoolView pool, Scene
             continue;
         }
         if (has) {
-            closest_round<COUNT>(sc, st, &wc);
+            closest_round<COUNT>(sc, st, stack, &wc);
             if (closest_done(st)) {
                 float t = st.d_min;
                 int id = st.id;
@@ -376,12 +378,13 @@ __global__ void __launch_bounds__(kFastBlock) k_extend_fast(PoolView pool, Scene
     if (replays) atomicAdd(&ctl->cnt_replays, (unsigned long long)replays);
 }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(kFastBlock) k_shadow_fast(PoolView pool, ShadowView sq, SceneDev sc, Control* ctl) {
+template <bool COUNT, int MINB>
+__global__ void __launch_bounds__(kFastBlock, MINB) k_shadow_fast(PoolView pool, ShadowView sq, SceneDev sc, Control* ctl) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int n_rays = ctl->n_shadow;
     ShadowState st;
+    ShadowStack stack;
     st.nsp = 0;
     st.tsp = 0;
     st.occluded = false;
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(kFastBlock) k_shadow_fast(PoolView pool, Shado
                     Ray r;
                     r.o = f3(o4.x, o4.y, o4.z);
                     r.d = f3(d4.x, d4.y, d4.z);
-                    shadow_begin(st, r, o4.w);
+                    shadow_begin(st, stack, r, o4.w);
                     has = true;
                     entry = my;
                 }
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(kFastBlock) k_shadow_fast(PoolView pool, Shado
             continue;
         }
         if (has) {
-            shadow_round<COUNT>(sc, st, &wc);
+            shadow_round<COUNT>(sc, st, stack, &wc);
             if (shadow_done(st)) {
                 if (!st.occluded) {
                     const int slot = f2i(sq.d[entry].w);
@@ -582,9 +585,23 @@ static void iteration_impl(const PoolView& pool, const ShadowView& sq, int* free
     if (MODE == TRT_TRAVERSE_FAST) {
         // persistent grids: enough CTAs to fill every SM, each warp pulls rays until the queue is dry
         const int fast_grid = dims.sms * dims.fast_blocks_per_sm;
-        k_extend_fast<COUNT><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
-        k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
-        k_shadow_fast<COUNT><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
+        switch (dims.fast_variant) {  // register budget of the persistent kernels (tuning knob)
+        case 4:
+            k_extend_fast<COUNT, 4><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
+            k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+            k_shadow_fast<COUNT, 4><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
+            break;
+        case 6:
+            k_extend_fast<COUNT, 6><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
+            k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+            k_shadow_fast<COUNT, 6><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
+            break;
+        default:
+            k_extend_fast<COUNT, 8><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
+            k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+            k_shadow_fast<COUNT, 8><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
+            break;
+        }
     } else {
         k_extend<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl, replay_list);
         k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);

@@ -66,6 +66,7 @@ struct JobParams {
 struct LaunchDims {
     int sms;
     int fast_blocks_per_sm;  // resident CTAs per SM of the persistent traversal kernels
+    int fast_variant;        // 4, 6 or 8: __launch_bounds__ min-blocks variant (register budget)
 };
 
 // ---- launchers (wavefront.cu) --------------------------------------------------------
