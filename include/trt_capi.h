@@ -47,8 +47,10 @@ typedef struct {
     int seed_base;
     int traversal;      /* TRT_TRAVERSE_* */
     int pool_paths;     /* wavefront pool size (paths in flight); 0 = auto */
-    int count_rays;     /* 1 = maintain ray / node counters (small cost) */
-    int reserved[2];
+    int count_rays;     /* 1 = also count node fetches / triangle tests (small cost); ray
+                           and sample counts are always maintained */
+    int time_kernels;   /* 1 = record CUDA events at every kernel boundary (see trt_kernel_times) */
+    int reserved[1];
 } trt_opts;
 
 /* Work counters accumulated since the last trt_reset_counters(). */
@@ -61,7 +63,20 @@ typedef struct {
     uint64_t replays;           /* closest-hit queries re-run in reference order (FAST mode) */
     uint64_t iterations;        /* wavefront iterations executed */
     uint64_t kernel_launches;   /* kernels launched by the library */
+    uint64_t nodes_closest;     /* node records fetched by closest-hit queries only */
+    uint64_t tris_closest;      /* triangle tests by closest-hit queries only */
 } trt_counters;
+
+/* Device time of the last trt_render per kernel family, from CUDA events recorded on the
+ * context's stream at every kernel boundary (trt_opts.time_kernels = 1). */
+typedef struct {
+    float regen_ms;    /* prepare + regenerate (RNG seeding, primary rays) */
+    float extend_ms;   /* closest-hit traversal  -- the dominant kernel */
+    float shade_ms;    /* material evaluation, queue compaction, accumulation */
+    float shadow_ms;   /* any-hit traversal */
+    int iterations;    /* launches of each kernel family that were timed */
+    int reserved[3];
+} trt_kernel_times;
 
 /* Device-side layout summary of the uploaded scene (for roofline bookkeeping). */
 typedef struct {
@@ -146,6 +161,7 @@ int trt_reset_counters(trt_ctx* ctx);
 /* Milliseconds the last trt_render spent between its first and last kernel,
  * measured with CUDA events on the context's stream (valid after synchronise). */
 int trt_last_render_ms(trt_ctx* ctx, float* ms);
+int trt_kernel_times_get(trt_ctx* ctx, trt_kernel_times* out);
 /* The CUDA stream (cudaStream_t) the context launches on, and a way to make it launch on a
  * caller-owned stream instead (NULL restores the context's own stream).  The reference
  * launches on the legacy default stream (src/renderer.cu:769). */

@@ -46,15 +46,24 @@ class TrtError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("max_depth", C.c_int), ("rr_threshold", C.c_int), ("seed_base", C.c_int),
                 ("traversal", C.c_int), ("pool_paths", C.c_int), ("count_rays", C.c_int),
-                ("reserved", C.c_int * 2)]
+                ("time_kernels", C.c_int), ("reserved", C.c_int * 1)]
 
 
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "closest_rays", "shadow_rays", "nodes_fetched",
-                                          "tris_tested", "replays", "iterations", "kernel_launches")]
+                                          "tris_tested", "replays", "iterations", "kernel_launches",
+                                          "nodes_closest", "tris_closest")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [("regen_ms", C.c_float), ("extend_ms", C.c_float), ("shade_ms", C.c_float),
+                ("shadow_ms", C.c_float), ("iterations", C.c_int), ("reserved", C.c_int * 3)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
 class SceneInfo(C.Structure):
@@ -346,6 +355,11 @@ class Context:
         ms = C.c_float()
         _check(lib().trt_last_render_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def kernel_times(self):
+        k = KernelTimes()
+        _check(lib().trt_kernel_times_get(self._h, C.byref(k)))
+        return k.as_dict()
 
     def stream(self):
         return lib().trt_stream(self._h)

@@ -89,6 +89,11 @@ struct trt_ctx {
     Control* d_ctl = nullptr;
     Control* h_ctl = nullptr;  // pinned, 2 entries
 
+    // per-kernel timing (trt_opts.time_kernels)
+    std::vector<cudaEvent_t> marks;  // 5 per timed iteration
+    size_t marks_used = 0;
+    trt_kernel_times ktimes{};
+
     // scratch accumulation buffer for trt_render_to_host
     float* d_accum_own = nullptr;
     size_t accum_own_bytes = 0;
@@ -261,6 +266,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_pool(c, o.pool_paths ? o.pool_paths : kDefaultPool)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
+    c->marks_used = 0;
     LaunchDims dims{c->sms, 8, 8};
     if (const char* e = getenv("TRT_FAST_VARIANT")) dims.fast_variant = atoi(e);
     dims.fast_blocks_per_sm = dims.fast_variant == 4 ? 4 : (dims.fast_variant == 6 ? 6 : 8);
@@ -279,9 +285,20 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         c->launches += 3;
         // Issue batches of iterations, staying one batch ahead of the completion poll.
         auto issue = [&](int slot) -> int {
-            for (int i = 0; i < kBatchIterations; i++)
+            for (int i = 0; i < kBatchIterations; i++) {
+                cudaEvent_t* marks = nullptr;
+                if (o.time_kernels) {
+                    while (c->marks.size() < c->marks_used + 5) {
+                        cudaEvent_t e;
+                        CU(cudaEventCreate(&e));
+                        c->marks.push_back(e);
+                    }
+                    marks = c->marks.data() + c->marks_used;
+                    c->marks_used += 5;
+                }
                 wf_iteration(c->pool, c->sq, c->d_free, c->d_replay, c->d_ctl, c->sc, job, o.traversal,
-                             o.count_rays != 0, dims, c->stream);
+                             o.count_rays != 0, dims, c->stream, marks);
+            }
             c->launches += (unsigned long long)kBatchIterations * kpi;
             CU(cudaMemcpyAsync(&c->h_ctl[slot], c->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaEventRecord(c->ev_poll[slot], c->stream));
@@ -365,6 +382,7 @@ int trt_destroy(trt_ctx* c) {
     cudaFree(c->d_ctl);
     cudaFreeHost(c->h_ctl);
     cudaFree(c->d_accum_own);
+    for (cudaEvent_t e : c->marks) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_begin);
     cudaEventDestroy(c->ev_end);
     cudaEventDestroy(c->ev_poll[0]);
@@ -595,6 +613,8 @@ int trt_get_counters(trt_ctx* c, trt_counters* out) {
     out->replays = hc.cnt_replays;
     out->iterations = hc.cnt_iterations;
     out->kernel_launches = c->launches;
+    out->nodes_closest = hc.cnt_nodes_closest;
+    out->tris_closest = hc.cnt_tris_closest;
     return 0;
 }
 
@@ -612,6 +632,25 @@ int trt_last_render_ms(trt_ctx* c, float* ms) {
     if (int rc = use_device(c)) return rc;
     CU(cudaEventSynchronize(c->ev_end));
     CU(cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+    return 0;
+}
+
+int trt_kernel_times_get(trt_ctx* c, trt_kernel_times* out) {
+    if (!c || !out) return fail(TRT_ERR_ARG, "null pointer");
+    if (int rc = use_device(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    trt_kernel_times t;
+    memset(&t, 0, sizeof(t));
+    for (size_t i = 0; i + 5 <= c->marks_used; i += 5) {
+        float ms[4];
+        for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], c->marks[i + k], c->marks[i + k + 1]));
+        t.regen_ms += ms[0];
+        t.extend_ms += ms[1];
+        t.shade_ms += ms[2];
+        t.shadow_ms += ms[3];
+        t.iterations++;
+    }
+    *out = t;
     return 0;
 }
 

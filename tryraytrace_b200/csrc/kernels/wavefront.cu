@@ -78,6 +78,7 @@ __global__ void k_reset_counters(Control* ctl) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->cnt_samples = ctl->cnt_closest = ctl->cnt_shadow = ctl->cnt_nodes = ctl->cnt_tris = 0;
     ctl->cnt_replays = ctl->cnt_iterations = 0;
+    ctl->cnt_nodes_closest = ctl->cnt_tris_closest = 0;
 }
 
 __global__ void k_init_pool(PoolView pool, int* free_list) {
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(kBlock) k_extend(PoolView pool, SceneDev sc, C
     if (COUNT) {
         atomicAdd(&ctl->cnt_nodes, nodes);
         atomicAdd(&ctl->cnt_tris, tris);
+        atomicAdd(&ctl->cnt_nodes_closest, nodes);
+        atomicAdd(&ctl->cnt_tris_closest, tris);
     }
     (void)replay_list;
 }
@@ -260,10 +263,9 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, ShadowView sq, 
         sq.d[si] = make_float4(io.shadow_ray.d.x, io.shadow_ray.d.y, io.shadow_ray.d.z, i2f(slot));
         sq.c[si] = make_float4(io.shadow_contrib.x, io.shadow_contrib.y, io.shadow_contrib.z, 0.f);
     }
-    if (COUNT) {
-        const unsigned m = __ballot_sync(0xffffffffu, cont);
-        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&ctl->cnt_closest, (unsigned long long)__popc(m));
-    }
+    // closest-hit rays issued for the next iteration (ray statistics are always maintained)
+    const int n_cont = __syncthreads_count(cont);
+    if (threadIdx.x == 0 && n_cont) atomicAdd(&ctl->cnt_closest, (unsigned long long)n_cont);
 }
 
 // ---- shadow: any hit for every queued shadow ray ----------------------------------------
@@ -374,6 +376,8 @@ __global__ void __launch_bounds__(kFastBlock, MINB) k_extend_fast(PoolView pool,
     if (COUNT) {
         atomicAdd(&ctl->cnt_nodes, (unsigned long long)wc.nodes);
         atomicAdd(&ctl->cnt_tris, (unsigned long long)wc.tris);
+        atomicAdd(&ctl->cnt_nodes_closest, (unsigned long long)wc.nodes);
+        atomicAdd(&ctl->cnt_tris_closest, (unsigned long long)wc.tris);
     }
     if (replays) atomicAdd(&ctl->cnt_replays, (unsigned long long)replays);
 }
@@ -577,47 +581,60 @@ int wf_kernels_per_iteration(int) { return 5; }
 
 template <int MODE, bool COUNT>
 static void iteration_impl(const PoolView& pool, const ShadowView& sq, int* free_list, int* replay_list, Control* ctl,
-                           const SceneDev& sc, const JobParams& job, const LaunchDims& dims, cudaStream_t s) {
+                           const SceneDev& sc, const JobParams& job, const LaunchDims& dims, cudaStream_t s,
+                           cudaEvent_t* marks) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
+    auto mark = [&](int i) { if (marks) cudaEventRecord(marks[i], s); };
+    mark(0);
     k_prepare<<<1, 32, 0, s>>>(ctl);
     k_regen<<<persistent < full ? persistent : full, kBlock, 0, s>>>(pool, free_list, ctl, job);
+    mark(1);
     if (MODE == TRT_TRAVERSE_FAST) {
         // persistent grids: enough CTAs to fill every SM, each warp pulls rays until the queue is dry
         const int fast_grid = dims.sms * dims.fast_blocks_per_sm;
         switch (dims.fast_variant) {  // register budget of the persistent kernels (tuning knob)
         case 4:
             k_extend_fast<COUNT, 4><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
+            mark(2);
             k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+            mark(3);
             k_shadow_fast<COUNT, 4><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
             break;
         case 6:
             k_extend_fast<COUNT, 6><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
+            mark(2);
             k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+            mark(3);
             k_shadow_fast<COUNT, 6><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
             break;
         default:
             k_extend_fast<COUNT, 8><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
+            mark(2);
             k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+            mark(3);
             k_shadow_fast<COUNT, 8><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
             break;
         }
     } else {
         k_extend<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl, replay_list);
+        mark(2);
         k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
+        mark(3);
         k_shadow<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sq, sc, ctl);
     }
+    mark(4);
 }
 
 void wf_iteration(const PoolView& pool, const ShadowView& sq, int* free_list, int* replay_list, Control* ctl,
                   const SceneDev& sc, const JobParams& job, int traversal, bool count, const LaunchDims& dims,
-                  cudaStream_t s) {
+                  cudaStream_t s, cudaEvent_t* marks) {
     if (traversal == TRT_TRAVERSE_REF) {
-        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s);
-        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s);
+        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
+        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
     } else {
-        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s);
-        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s);
+        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
+        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
     }
 }
 

@@ -47,7 +47,9 @@ struct Control {
     int cursor_extend, cursor_shadow, cursor_replay;
     int n_replay;
     // counters (see trt_counters)
-    unsigned long long cnt_samples, cnt_closest, cnt_shadow, cnt_nodes, cnt_tris, cnt_replays, cnt_iterations;
+    unsigned long long cnt_samples, cnt_closest, cnt_shadow, cnt_replays, cnt_iterations;
+    unsigned long long cnt_nodes, cnt_tris;                // all queries (COUNT builds only)
+    unsigned long long cnt_nodes_closest, cnt_tris_closest;  // closest-hit queries only
 };
 
 // Per-job constants handed to the kernels by value.
@@ -76,9 +78,11 @@ void wf_begin_job(Control* ctl, unsigned long long total_samples, int pool_capac
 void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_frame_seed, int frame_stride,
                   int seed_base, int n_frames, XwColVec* out, cudaStream_t s);
 // one wavefront iteration (five kernels) on stream s
+// `marks`, when not null, receives five events recorded at the kernel boundaries of the
+// iteration: [prepare+regenerate] m1 [extend] m2 [shade] m3 [shadow] m4  (m0 first).
 void wf_iteration(const PoolView& pool, const ShadowView& sq, int* free_list, int* replay_list, Control* ctl,
                   const SceneDev& sc, const JobParams& job, int traversal, bool count, const LaunchDims& dims,
-                  cudaStream_t s);
+                  cudaStream_t s, cudaEvent_t* marks = nullptr);
 int wf_kernels_per_iteration(int traversal);
 
 void wf_trace_primary(const SceneDev& sc, const JobParams& job, int frame_seed, int traversal, int* d_id, float* d_t,
