@@ -1,4 +1,6 @@
-"""Render one config once (for profiling).  Usage: render_once.py config spp pool fast|ref [warm_spp]"""
+"""Render one config once (for profiling / tuning).
+Usage: render_once.py config spp pool fast|ref [warm_spp] [time_kernels]
+Prints ms per sample-per-pixel, Mrays/s and (with time_kernels=1) the per-kernel-family split."""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -7,13 +9,24 @@ import torch
 import tryraytrace_b200 as trt
 config, spp, pool, mode = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
 warm = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+timed = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 sc = trt.HostScene.from_config(config)
 cam, w, h = trt.config_camera(config)
 ctx = trt.Context(0)
 ctx.upload(sc)
 acc = torch.zeros(w * h * 4, device="cuda")
-o = trt.default_opts(traversal=trt.TRAVERSE_REF if mode == "ref" else trt.TRAVERSE_FAST, pool_paths=pool)
+trav = trt.TRAVERSE_REF if mode == "ref" else trt.TRAVERSE_FAST
+o = trt.default_opts(traversal=trav, pool_paths=pool)
 if warm:
     ctx.render(acc, w, h, 1, warm, cam, o); ctx.synchronize()
-ctx.render(acc, w, h, 1, spp, cam, o); ctx.synchronize()
-print("ms/spp", ctx.last_render_ms() / spp, "mean", float(acc.view(-1, 4)[:, :3].mean()) / (spp + warm))
+ctx.reset_counters()
+ot = trt.default_opts(traversal=trav, pool_paths=pool, time_kernels=timed)
+ctx.render(acc, w, h, 1 + warm, spp, cam, ot); ctx.synchronize()
+ms = ctx.last_render_ms()
+c = ctx.counters()
+rays = c["closest_rays"] + c["shadow_rays"]
+line = f"ms/spp {ms / spp:.3f} Mrays/s {rays / ms / 1e3:.0f} rays/sample {rays / max(c['samples'], 1):.3f} iters {c['iterations']} replays {c['replays']}"
+if timed:
+    k = ctx.kernel_times()
+    line += " | " + " ".join(f"{n[:-3]} {k[n]:.1f}" for n in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms"))
+print(line, "mean", float(acc.view(-1, 4)[:, :3].mean()) / (spp + warm))

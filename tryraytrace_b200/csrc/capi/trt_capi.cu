@@ -66,7 +66,6 @@ struct trt_ctx {
     int* d_lights = nullptr;
     float4* d_wide_nodes = nullptr;
     float4* d_tris = nullptr;
-    float4* d_leaf_box = nullptr;
     std::vector<cudaArray_t> tex_arrays;
     std::vector<cudaTextureObject_t> tex_objs;
     SceneDev sc{};
@@ -83,9 +82,12 @@ struct trt_ctx {
     int pool_cap = 0;
     void* pool_mem = nullptr;
     PoolView pool{};
-    ShadowView sq{};
     int* d_free = nullptr;
-    int* d_replay = nullptr;
+    // scratch pool of the parity entry points (FAST mode runs the production kernels over it)
+    int scratch_cap = 0;
+    void* scratch_mem = nullptr;
+    PoolView scratch{};
+    size_t smem_limit = 0;  // opt-in shared memory per block
     Control* d_ctl = nullptr;
     Control* h_ctl = nullptr;  // pinned, 2 entries
 
@@ -116,8 +118,7 @@ void free_scene(trt_ctx* c) {
     cudaFree(c->d_lights);
     cudaFree(c->d_wide_nodes);
     cudaFree(c->d_tris);
-    cudaFree(c->d_leaf_box);
-    c->d_objects = c->d_ref_nodes = c->d_wide_nodes = c->d_tris = c->d_leaf_box = nullptr;
+    c->d_objects = c->d_ref_nodes = c->d_wide_nodes = c->d_tris = nullptr;
     c->d_lights = nullptr;
     c->have_scene = false;
 }
@@ -195,34 +196,73 @@ int ensure_col_vecs(trt_ctx* c, size_t entries) {
     return 0;
 }
 
+// One allocation, carved into the SoA arrays of PoolView (+ the free list when asked for).
+int alloc_pool(int cap, bool with_free_list, void** mem, PoolView* pool, int** free_list) {
+    const size_t n = (size_t)cap;
+    // 8 float4/uint4 arrays + hit (float2) + rng_b (uint2) + free list (int)
+    const size_t bytes = n * (8 * 16 + 2 * 8 + (with_free_list ? 4 : 0));
+    CU(cudaMalloc(mem, bytes));
+    char* p = (char*)*mem;
+    auto take = [&](size_t b) { void* r = p; p += b; return r; };
+    pool->ray_o = (float4*)take(n * 16);
+    pool->ray_d = (float4*)take(n * 16);
+    pool->thr = (float4*)take(n * 16);
+    pool->rad = (float4*)take(n * 16);
+    pool->pend = (float4*)take(n * 16);
+    pool->sh_o = (float4*)take(n * 16);
+    pool->sh_d = (float4*)take(n * 16);
+    pool->rng_a = (uint4*)take(n * 16);
+    pool->hit = (float2*)take(n * 8);
+    pool->rng_b = (uint2*)take(n * 8);
+    if (free_list) *free_list = with_free_list ? (int*)take(n * 4) : nullptr;
+    pool->capacity = cap;
+    return 0;
+}
+
 int ensure_pool(trt_ctx* c, int cap) {
     cap = std::max(256, (cap + 255) & ~255);
     if (c->pool_cap == cap) return 0;
     cudaFree(c->pool_mem);
     c->pool_mem = nullptr;
     c->pool_cap = 0;
-    const size_t n = (size_t)cap;
-    // ray_o, ray_d, thr, rad (float4) + rng_a (uint4) + shadow o,d,c (float4): 8 x 16 B
-    // hit (float2), rng_b (uint2): 2 x 8 B; free list, replay list: 2 x 4 B
-    const size_t bytes = n * (8 * 16 + 2 * 8 + 2 * 4);
-    CU(cudaMalloc(&c->pool_mem, bytes));
-    char* p = (char*)c->pool_mem;
-    auto take = [&](size_t b) { void* r = p; p += b; return r; };
-    c->pool.ray_o = (float4*)take(n * 16);
-    c->pool.ray_d = (float4*)take(n * 16);
-    c->pool.thr = (float4*)take(n * 16);
-    c->pool.rad = (float4*)take(n * 16);
-    c->pool.rng_a = (uint4*)take(n * 16);
-    c->sq.o = (float4*)take(n * 16);
-    c->sq.d = (float4*)take(n * 16);
-    c->sq.c = (float4*)take(n * 16);
-    c->pool.hit = (float2*)take(n * 8);
-    c->pool.rng_b = (uint2*)take(n * 8);
-    c->d_free = (int*)take(n * 4);
-    c->d_replay = (int*)take(n * 4);
-    c->pool.capacity = cap;
+    if (int rc = alloc_pool(cap, true, &c->pool_mem, &c->pool, &c->d_free)) return rc;
     c->pool_cap = cap;
     return 0;
+}
+
+int ensure_scratch(trt_ctx* c, int n) {
+    const int cap = std::max(256, (n + 255) & ~255);
+    if (c->scratch_cap >= cap) {
+        c->scratch.capacity = cap;
+        return 0;
+    }
+    cudaFree(c->scratch_mem);
+    c->scratch_mem = nullptr;
+    c->scratch_cap = 0;
+    if (int rc = alloc_pool(cap, false, &c->scratch_mem, &c->scratch, nullptr)) return rc;
+    c->scratch_cap = cap;
+    return 0;
+}
+
+// Launch configuration of the persistent traversal kernels.  Defaults: 512-thread CTAs, as much
+// of the top of the tree in shared memory as fits beside the stacks while leaving L1 room for
+// the triangle records.  TRT_FAST_THREADS / TRT_SMEM_NODES / TRT_REFILL override (tuning).
+LaunchDims launch_dims(const trt_ctx* c) {
+    LaunchDims d;
+    d.sms = c->sms;
+    d.fast_threads = 512;
+    if (const char* e = getenv("TRT_FAST_THREADS")) {
+        const int v = atoi(e);
+        if (v == 512 || v == 768 || v == 1024) d.fast_threads = v;
+    }
+    const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
+    d.smem_nodes = std::min(fit, 768);
+    if (const char* e = getenv("TRT_SMEM_NODES")) d.smem_nodes = std::max(0, std::min(fit, atoi(e)));
+    d.refill_below = 25;
+    if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
+    d.tri_min = 1;
+    if (const char* e = getenv("TRT_TRI_MIN")) d.tri_min = std::max(1, std::min(32, atoi(e)));
+    return d;
 }
 
 void fill_job(trt_ctx* c, JobParams& job, float* d_accum, int w, int h, int first_frame_seed, int n_frames,
@@ -267,10 +307,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
     c->marks_used = 0;
-    LaunchDims dims{c->sms, 8, 8};
-    if (const char* e = getenv("TRT_FAST_VARIANT")) dims.fast_variant = atoi(e);
-    dims.fast_blocks_per_sm = dims.fast_variant == 4 ? 4 : (dims.fast_variant == 6 ? 6 : 8);
-    if (const char* e = getenv("TRT_FAST_BLOCKS")) dims.fast_blocks_per_sm = std::max(1, atoi(e));
+    const LaunchDims dims = launch_dims(c);
     const int kpi = wf_kernels_per_iteration(o.traversal);
     CU(cudaEventRecord(c->ev_begin, c->stream));
     const unsigned long long pixels = (unsigned long long)w * h;
@@ -296,8 +333,8 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
                     marks = c->marks.data() + c->marks_used;
                     c->marks_used += 5;
                 }
-                wf_iteration(c->pool, c->sq, c->d_free, c->d_replay, c->d_ctl, c->sc, job, o.traversal,
-                             o.count_rays != 0, dims, c->stream, marks);
+                wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, job, o.traversal, o.count_rays != 0, dims,
+                             c->stream, marks);
             }
             c->launches += (unsigned long long)kBatchIterations * kpi;
             CU(cudaMemcpyAsync(&c->h_ctl[slot], c->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
@@ -357,6 +394,13 @@ int trt_create(int device, trt_ctx** out) {
     c->device = device;
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+    int smem_optin = 0;
+    CU(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    c->smem_limit = (size_t)smem_optin;
+    if (wf_configure() != 0) {
+        cudaGetLastError();
+        return fail(TRT_ERR_CUDA, "cannot opt in to %d bytes of shared memory per block", smem_optin);
+    }
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev_begin));
@@ -379,6 +423,7 @@ int trt_destroy(trt_ctx* c) {
     cudaFree(c->d_col_pows);
     cudaFree(c->d_col_vecs);
     cudaFree(c->pool_mem);
+    cudaFree(c->scratch_mem);
     cudaFree(c->d_ctl);
     cudaFreeHost(c->h_ctl);
     cudaFree(c->d_accum_own);
@@ -443,8 +488,6 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
     CU(cudaMemcpy(c->d_wide_nodes, wb.nodes.data(), wb.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
     CU(cudaMalloc(&c->d_tris, std::max<size_t>(wb.tris.size(), 1) * sizeof(TriRecord)));
     CU(cudaMemcpy(c->d_tris, wb.tris.data(), wb.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&c->d_leaf_box, (size_t)n_objects * 32));
-    CU(cudaMemcpy(c->d_leaf_box, wb.leaf_boxes.data(), (size_t)n_objects * 32, cudaMemcpyHostToDevice));
 
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
@@ -458,7 +501,6 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
     for (int i = 0; i < n_textures; i++) sc.tex[i] = c->tex_objs[i];
     sc.wide_nodes = c->d_wide_nodes;
     sc.tris = c->d_tris;
-    sc.leaf_box = c->d_leaf_box;
     sc.n_wide_nodes = (int)wb.nodes.size();
     sc.n_tris = (int)wb.tris.size();
 
@@ -525,8 +567,10 @@ int trt_trace_primary(trt_ctx* c, int w, int h, int frame_seed, const void* cam,
     o.seed_base = seed_base;
     JobParams job;
     fill_job(c, job, nullptr, w, h, frame_seed, 1, 1, cam, o);
+    if (int rc = ensure_scratch(c, w * h)) return rc;
     wf_col_table(c->d_col_pows, c->n_col_bits, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
-    wf_trace_primary(c->sc, job, frame_seed, traversal, d_id, d_t, d_ray, d_fetched, d_entered, d_tris, c->stream);
+    wf_trace_primary(c->sc, job, frame_seed, traversal, d_id, d_t, d_ray, d_fetched, d_entered, d_tris, c->scratch,
+                     c->d_ctl, launch_dims(c), c->stream);
     c->launches += 2;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -538,7 +582,8 @@ int trt_trace_closest(trt_ctx* c, const float* d_rays, int n, int traversal, int
     if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
     if (n <= 0) return 0;
     if (int rc = use_device(c)) return rc;
-    wf_trace_closest(c->sc, d_rays, n, traversal, d_id, d_t, c->stream);
+    if (int rc = ensure_scratch(c, n)) return rc;
+    wf_trace_closest(c->sc, d_rays, n, traversal, d_id, d_t, c->scratch, c->d_ctl, launch_dims(c), c->stream);
     c->launches += 1;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -550,7 +595,8 @@ int trt_trace_shadow(trt_ctx* c, const float* d_rays, int n, int traversal, int*
     if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
     if (n <= 0) return 0;
     if (int rc = use_device(c)) return rc;
-    wf_trace_shadow(c->sc, d_rays, n, traversal, d_occ, c->stream);
+    if (int rc = ensure_scratch(c, n)) return rc;
+    wf_trace_shadow(c->sc, d_rays, n, traversal, d_occ, c->scratch, c->d_ctl, launch_dims(c), c->stream);
     c->launches += 1;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());

@@ -147,11 +147,21 @@ void clear_node(WideNode& w) {
     }
 }
 
-// single rounding, denormal results flushed like the device's FADD.FTZ
-float sub_ftz(float a, float b) {
-    float r = a - b;
-    if (std::fabs(r) < 1.17549435e-38f) r = std::copysign(0.f, r);
-    return r;
+// single rounding, denormal inputs and results flushed like the device's FADD.FTZ
+float ftz(float r) { return std::fabs(r) < 1.17549435e-38f ? std::copysign(0.f, r) : r; }
+float add_ftz(float a, float b) { return ftz(ftz(a) + ftz(b)); }
+
+// The leaf box the traversal kernels derive from a triangle's vertices (kernels/traverse_fast.cuh
+// derive_leaf_box; the rule of reference src/bvh.cpp:12-30), evaluated the way the device does.
+void derived_leaf_box(const Object& o, float mn[3], float mx[3]) {
+    const float v[3][3] = {{o.v0.x, o.v0.y, o.v0.z}, {o.v1.x, o.v1.y, o.v1.z}, {o.v2.x, o.v2.y, o.v2.z}};
+    for (int k = 0; k < 3; k++) {
+        float lo = ftz(std::fmin(std::fmin(v[0][k], v[1][k]), v[2][k]));  // FMNMX.FTZ on the device
+        float hi = ftz(std::fmax(std::fmax(v[0][k], v[1][k]), v[2][k]));
+        if (add_ftz(hi, -lo) < 1e-3f) { lo = add_ftz(lo, -1e-3f); hi = add_ftz(hi, 1e-3f); }
+        mn[k] = lo;
+        mx[k] = hi;
+    }
 }
 
 }  // namespace
@@ -162,6 +172,7 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
     out.tris.clear();
     out.leaf_boxes.assign(n_objects, LeafBox{{INFINITY, INFINITY, INFINITY, 0}, {-INFINITY, -INFINITY, -INFINITY, 0}});
     out.n_top_prims = 0;
+    out.n_underivable = 0;
     out.depth = 0;
 
     // 1. reference leaf box of every object (objects no leaf refers to can never be hit)
@@ -290,10 +301,18 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
         const Object& o = objects[order[i]];
         TriRecord& t = out.tris[i];
         t.v0[0] = o.v0.x; t.v0[1] = o.v0.y; t.v0[2] = o.v0.z;
-        t.id = order[i];
-        t.e1[0] = sub_ftz(o.v1.x, o.v0.x); t.e1[1] = sub_ftz(o.v1.y, o.v0.y); t.e1[2] = sub_ftz(o.v1.z, o.v0.z);
-        t.e2[0] = sub_ftz(o.v2.x, o.v0.x); t.e2[1] = sub_ftz(o.v2.y, o.v0.y); t.e2[2] = sub_ftz(o.v2.z, o.v0.z);
+        t.v1[0] = o.v1.x; t.v1[1] = o.v1.y; t.v1[2] = o.v1.z;
+        t.v2[0] = o.v2.x; t.v2[1] = o.v2.y; t.v2[2] = o.v2.z;
         t.pad1 = t.pad2 = 0.f;
+        // the kernels re-derive the reference leaf box from the vertices; where that does not
+        // reproduce the uploaded leaf node exactly (a foreign builder, NaNs), flag the triangle
+        float mn[3], mx[3];
+        derived_leaf_box(o, mn, mx);
+        const Box& lb = pbox[order[i]];
+        bool same = true;
+        for (int k = 0; k < 3; k++) same = same && mn[k] == lb.mn[k] && mx[k] == lb.mx[k];
+        t.id = order[i] | (same ? 0 : kTriNoDeriveBit);
+        if (!same) out.n_underivable++;
     }
 
     // 6. collapse the binary tree into 4-wide nodes
@@ -311,11 +330,15 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
         out.depth = 1;
         return;
     }
-    struct Work { int bnode; int wide; int depth; };
-    std::vector<Work> work;
+    // Nodes are emitted in descending box area (a proxy for how often rays visit them), so the
+    // first k nodes are the ones worth staging into shared memory.
+    struct Work { int bnode; int wide; int depth; float area; };
+    auto colder = [](const Work& a, const Work& b) { return a.area < b.area; };
+    std::vector<Work> work;  // max-heap on area
     out.nodes.emplace_back();
-    work.push_back(Work{root, 0, 1});
+    work.push_back(Work{root, 0, 1, bn[root].box.area()});
     while (!work.empty()) {
+        std::pop_heap(work.begin(), work.end(), colder);
         const Work wk = work.back();
         work.pop_back();
         out.depth = std::max(out.depth, wk.depth);
@@ -347,7 +370,8 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
                 const int idx = (int)out.nodes.size();
                 out.nodes.emplace_back();
                 w.child[k] = idx;
-                work.push_back(Work{kids[k], idx, wk.depth + 1});
+                work.push_back(Work{kids[k], idx, wk.depth + 1, b.area()});
+                std::push_heap(work.begin(), work.end(), colder);
             }
         }
         out.nodes[wk.wide] = w;

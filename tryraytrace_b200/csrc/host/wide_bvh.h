@@ -8,10 +8,13 @@
 //     strict superset of the reference traversal (kernels/traverse_wide.cuh);
 //   * oversized primitives (the room's one-triangle walls) lifted out of
 //     the SAH tree and attached near the root, where they stop inflating every upper box;
-//   * 48-byte triangle records (v0, e1, e2 as three float4) in wide-leaf order, e1/e2
-//     pre-subtracted with the same single rounding the reference applies per test;
-//   * the reference leaf box of every object (2 x float4), used to decide exactly whether
-//     the reference traversal would have reached a candidate triangle.
+//   * 48-byte triangle records (v0, v1, v2 as three float4) in wide-leaf order; the kernels
+//     subtract the edges per test exactly as the reference does, and re-derive the reference
+//     leaf box (bounds of the three vertices + the builder's padding rule) to decide exactly
+//     whether the reference traversal would have reached a candidate triangle.  A triangle
+//     whose uploaded leaf box is NOT reproduced by that rule carries kTriNoDeriveBit in its id
+//     word and is always resolved by the reference-order replay;
+//   * the reference leaf box of every object (host side only: builder input, tests).
 #pragma once
 #include "bvh.h"
 #include "scene.h"
@@ -29,12 +32,14 @@ struct WideNode {  // 128 bytes
 };
 static_assert(sizeof(WideNode) == 128, "WideNode layout");
 
+constexpr int kTriNoDeriveBit = 0x40000000;
+
 struct TriRecord {  // 48 bytes
     float v0[3];
-    int id;  // object index (position in the reference-sorted array)
-    float e1[3];
+    int id;  // object index (position in the reference-sorted array) | kTriNoDeriveBit
+    float v1[3];
     float pad1;
-    float e2[3];
+    float v2[3];
     float pad2;
 };
 static_assert(sizeof(TriRecord) == 48, "TriRecord layout");
@@ -48,6 +53,7 @@ struct WideBvh {
     std::vector<TriRecord> tris;
     std::vector<LeafBox> leaf_boxes;  // per object id
     int n_top_prims = 0;
+    int n_underivable = 0;  // triangles flagged kTriNoDeriveBit
     int depth = 0;
 };
 

@@ -73,8 +73,7 @@ struct SceneDev {
     cudaTextureObject_t tex[5];
     // re-laid-out arrays for the fast path
     const float4* wide_nodes;  // 8 float4 per 4-wide node (128 B)
-    const float4* tris;        // 3 float4 per triangle in wide-leaf order: (v0, id) (e1, -) (e2, -)
-    const float4* leaf_box;    // 2 float4 per object id: the reference leaf box (min, max)
+    const float4* tris;        // 3 float4 per triangle in wide-leaf order: (v0, id | flags) (v1, -) (v2, -)
     int n_wide_nodes, n_tris;
 };
 

@@ -1,0 +1,457 @@
+// traverse_fast.cuh -- TRAVERSE_FAST: ordered traversal of the 4-wide BVH with an exact accept
+// rule, so that the result equals the reference traversal's (reference src/renderer.cu:371-425
+// closest hit, :273-314 any hit) without visiting its ~60-80 nodes per ray.
+//
+// Why the result is the same (DESIGN.md "exactness argument"):
+//  1. Superset.  Every wide box contains the reference leaf boxes below it, and the slab test
+//     here is the reference's own formula -- (plane - o) * inv, a rounded subtract then a rounded
+//     multiply, with the same o and inv.  Both roundings are monotone, so a wider box can only
+//     give an earlier entry and a later exit: whenever the reference's test of a leaf box passes,
+//     the tests of all wide boxes above that triangle pass too.
+//  2. Same triangle arithmetic.  Candidates are tested with the reference's Moeller-Trumbore
+//     operation sequence on the original vertices (edges are re-subtracted per test, exactly as
+//     reference :239-240 does).
+//  3. Exact reachability.  The reference tests triangle k only if the slab tests of all its
+//     ancestors pass.  Ancestor boxes contain the leaf box, so by (1) they pass whenever the leaf
+//     box passes with entry < t_k; a candidate whose reference leaf box fails outright can never
+//     be reached by the reference and is dropped.  The leaf box is re-derived from the three
+//     vertices with the builder's rule (reference src/bvh.cpp:12-30); the upload verifies per
+//     triangle that this reproduces the uploaded leaf node bit for bit and flags the triangle
+//     otherwise (kTriNoDerive), which forces the replay below.
+//  4. Ambiguity.  The only order-dependent case left is a candidate whose leaf-box entry is not
+//     below its own hit distance (the reference culls against the running d_min, which depends
+//     on visit order).  Such rays are flagged and re-run through TRAVERSE_REF.  Ties in t resolve
+//     to the lowest object index, as the reference's ascending leaf order does.
+// Any-hit queries have a fixed interval, so (3) decides them exactly and no replay exists.
+//
+// Execution model (kernels in wavefront.cu).  One persistent CTA per SM.  A warp holds 32 rays;
+// the traversal is written as ROUNDS so the lanes stay converged: in every round a lane performs
+// at most one wide-node step (four child-box tests) and at most one triangle step.  Inner
+// children go to a per-lane node stack, leaf children to a separate per-lane triangle stack;
+// both live in SHARED memory (lane-interleaved, conflict free), with a local-memory overflow
+// that only deep trees ever touch.  The top of the tree (the first k nodes, emitted by the
+// builder in descending box area) is staged into shared memory once per CTA.  Rays arrive in
+// chunks of 32 through a per-warp double buffer filled by TMA bulk copies (cp.async.bulk +
+// mbarrier), so the refill of idle lanes never waits on HBM.
+#pragma once
+#include "common.cuh"
+#include "traverse_ref.cuh"
+
+namespace trt {
+
+struct WideCounts {
+    uint32_t nodes, tris;
+};
+
+constexpr int kWideEmptyRef = 0x7fffffff;
+constexpr int kSpillEntries = 48;  // logical node stack bound: 3 * wide depth + 1 (checked at upload)
+constexpr float kCullSlack = 1.0005f;
+constexpr int kTriIdMask = 0x3fffffff;
+constexpr int kTriNoDerive = 0x40000000;  // leaf box cannot be re-derived from the vertices: replay
+
+// ---- async staging primitives (sm_90+/sm_100 PTX) ----------------------------------------------
+TRT_DEV uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+TRT_DEV void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+TRT_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+TRT_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+TRT_DEV bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`
+TRT_DEV void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+// Per-lane traversal stacks live in shared memory and are addressed with 32-bit shared-window
+// addresses.  All stack accesses are volatile asm WITHOUT a memory clobber: they stay ordered
+// among themselves (pushes and pops never swap), while the compiler remains free to schedule
+// the global node/triangle loads across them.  Pushes are predicated stores, not branches.
+TRT_DEV void sts64_if(bool p, uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.u32 q, %0, 0;\n\t"
+        "@q st.shared.v2.u32 [%1], {%2, %3};\n\t}" ::"r"((uint32_t)p),
+        "r"(addr), "r"(x), "r"(y));
+}
+TRT_DEV void sts32_if(bool p, uint32_t addr, uint32_t x) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.u32 q, %0, 0;\n\t"
+        "@q st.shared.u32 [%1], %2;\n\t}" ::"r"((uint32_t)p),
+        "r"(addr), "r"(x));
+}
+TRT_DEV uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+TRT_DEV uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// streaming (evict-first) stores for results that are read once by the next kernel
+TRT_DEV void st_cs_f2(float2* p, float2 v) { __stcs(p, v); }
+
+// ---- geometry helpers --------------------------------------------------------------------------
+// The reference leaf box of a triangle: bounds of the three vertices, padded by 1e-3 on axes
+// thinner than 1e-3 (reference src/bvh.cpp:12-30).  min/max of finite values do not depend on
+// the order or on the instruction used; the three adds are single roundings like the host's.
+TRT_DEV void derive_leaf_box(const F3 v0, const F3 v1, const F3 v2, float4* bmin, float4* bmax) {
+    const float pad = 1e-3f;
+    float lx = fminf(fminf(v0.x, v1.x), v2.x), hx = fmaxf(fmaxf(v0.x, v1.x), v2.x);
+    float ly = fminf(fminf(v0.y, v1.y), v2.y), hy = fmaxf(fmaxf(v0.y, v1.y), v2.y);
+    float lz = fminf(fminf(v0.z, v1.z), v2.z), hz = fmaxf(fmaxf(v0.z, v1.z), v2.z);
+    if (p_sub(hx, lx) < pad) { lx = p_sub(lx, pad); hx = p_add(hx, pad); }
+    if (p_sub(hy, ly) < pad) { ly = p_sub(ly, pad); hy = p_add(hy, pad); }
+    if (p_sub(hz, lz) < pad) { lz = p_sub(lz, pad); hz = p_add(hz, pad); }
+    *bmin = make_float4(lx, ly, lz, 0.f);
+    *bmax = make_float4(hx, hy, hz, 0.f);
+}
+
+// The reference's leaf-box test for a closest-hit ray, from sign-selected planes: with a finite
+// inverse direction no NaN can occur, and min/max of the two plane products are then simply the
+// near/far products.  Returns whether the box passes independently of d_min (exit >= entry and
+// exit > 0) and the entry distance.
+TRT_DEV bool leaf_box_reach(const float4 bmin, const float4 bmax, const F3 o, const F3 inv, bool sx, bool sy, bool sz,
+                            float* entry) {
+    const float ax = p_mul(p_sub(sx ? bmax.x : bmin.x, o.x), inv.x), bx = p_mul(p_sub(sx ? bmin.x : bmax.x, o.x), inv.x);
+    const float ay = p_mul(p_sub(sy ? bmax.y : bmin.y, o.y), inv.y), by = p_mul(p_sub(sy ? bmin.y : bmax.y, o.y), inv.y);
+    const float az = p_mul(p_sub(sz ? bmax.z : bmin.z, o.z), inv.z), bz = p_mul(p_sub(sz ? bmin.z : bmax.z, o.z), inv.z);
+    const float tn = fmaxf(fmaxf(ax, ay), az);
+    const float tf = fminf(fminf(bx, by), bz);
+    *entry = tn;
+    return tf >= tn && tf > 0.f;
+}
+
+// Moeller-Trumbore with the reference's operation sequence (traverse_ref.cuh ref_tri_edges),
+// evaluated without branches: every early-out of reference :235-268 becomes one term of `ok`,
+// with the same comparisons, so NaN/inf intermediates are rejected exactly where the reference
+// rejects them.
+TRT_DEV float tri_test_flat(const F3 v0, const F3 e1, const F3 e2, const F3 o, const F3 d) {
+    const float eps = 1e-5f;
+    const F3 h = x_cross(d, e2);
+    const float a = x_dot(e1, h);
+    const float f = p_rcp(a);
+    const F3 s = x_sub(o, v0);
+    const float u = p_mul(f, x_dot(s, h));
+    const F3 q = x_cross(s, e1);
+    const float v = p_mul(f, x_dot(d, q));
+    const float t = p_mul(f, x_dot(e2, q));
+    const bool ok = !(a > -eps && a < eps) && !(u < 0.f || u > 1.f) && !(v < 0.f || p_add(u, v) > 1.f) && t > eps;
+    return ok ? t : 0.f;
+}
+
+// Slab interval of one child from its near/far planes (selected by the sign of the inverse
+// direction when the node was loaded), clamped to [lo_clamp, hi_clamp]; `<=` instead of the
+// reference's strict tests only ever adds candidates (superset).
+TRT_DEV bool child_interval(float nx, float fx, float ny, float fy, float nz, float fz, const F3 o, const F3 inv,
+                            float lo_clamp, float hi_clamp, float* t_near) {
+    const float ax = p_mul(p_sub(nx, o.x), inv.x), bx = p_mul(p_sub(fx, o.x), inv.x);
+    const float ay = p_mul(p_sub(ny, o.y), inv.y), by = p_mul(p_sub(fy, o.y), inv.y);
+    const float az = p_mul(p_sub(nz, o.z), inv.z), bz = p_mul(p_sub(fz, o.z), inv.z);
+    const float tn = fmaxf(fmaxf(ax, ay), fmaxf(az, lo_clamp));
+    const float tf = fminf(fminf(bx, by), fminf(bz, hi_clamp));
+    *t_near = tn;
+    return tn <= tf;
+}
+
+// One 4-wide node: near/far plane vectors per axis and the child references.
+struct NodeData {
+    float4 nx, fx, ny, fy, nz, fz;
+    int4 ch;
+};
+
+// `near_off` packs the byte offsets of the near-plane vectors inside the 128-byte node:
+// x: 0 or 16, y: 32 or 48, z: 64 or 80; the far plane is the other one of each pair (^16).
+TRT_DEV void load_node(NodeData& n, const unsigned char* s_nodes, int k_smem, const float4* g_nodes, int node, int nxo,
+                       int nyo, int nzo) {
+    if (node < k_smem) {
+        const unsigned char* b = s_nodes + node * 128;
+        n.nx = *reinterpret_cast<const float4*>(b + nxo);
+        n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
+        n.ny = *reinterpret_cast<const float4*>(b + nyo);
+        n.fy = *reinterpret_cast<const float4*>(b + (nyo ^ 16));
+        n.nz = *reinterpret_cast<const float4*>(b + nzo);
+        n.fz = *reinterpret_cast<const float4*>(b + (nzo ^ 16));
+        n.ch = *reinterpret_cast<const int4*>(b + 96);
+    } else {
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(g_nodes) + (size_t)node * 128;
+        n.nx = __ldg(reinterpret_cast<const float4*>(b + nxo));
+        n.fx = __ldg(reinterpret_cast<const float4*>(b + (nxo ^ 16)));
+        n.ny = __ldg(reinterpret_cast<const float4*>(b + nyo));
+        n.fy = __ldg(reinterpret_cast<const float4*>(b + (nyo ^ 16)));
+        n.nz = __ldg(reinterpret_cast<const float4*>(b + nzo));
+        n.fz = __ldg(reinterpret_cast<const float4*>(b + (nzo ^ 16)));
+        n.ch = __ldg(reinterpret_cast<const int4*>(b + 96));
+    }
+}
+
+// ---- closest hit -------------------------------------------------------------------------------
+// Stack geometry of one lane: S entries of E bytes, entry j at base + j * E (E = entry size x
+// CTA threads, so a warp's accesses are conflict free).  Node entries grow up from `base`,
+// triangle entries grow down from `base + (S-1) * E`; np / tp are the next free entries.
+struct ClosestRay {
+    F3 o, d, inv;
+    float d_min;
+    int id;
+    int cur;            // next inner node to open (held in a register), or kWideEmptyRef
+    int nxo, nyo, nzo;  // near-plane byte offsets (see load_node)
+    uint32_t np, tp;    // shared-window addresses of the next free node / triangle entry
+    int nspill;         // entries in the local overflow
+    bool amb;
+};
+
+TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, uint32_t base, uint32_t ttop) {
+    s.o = f3(o4.x, o4.y, o4.z);
+    s.d = f3(d4.x, d4.y, d4.z);
+    s.inv = f3(ref_safe_inv(s.d.x), ref_safe_inv(s.d.y), ref_safe_inv(s.d.z));
+    s.nxo = s.inv.x < 0.f ? 16 : 0;
+    s.nyo = s.inv.y < 0.f ? 48 : 32;
+    s.nzo = s.inv.z < 0.f ? 80 : 64;
+    s.d_min = 1e20f;
+    s.id = -1;
+    s.amb = false;
+    s.np = base;
+    s.tp = ttop;
+    s.nspill = 0;
+    s.cur = 0;  // root
+}
+
+// One round for one lane; called by ALL lanes of the warp (a lane without a ray has empty stacks
+// and nothing happens for it).  E = bytes between consecutive entries of this lane, S = entries.
+// `tri_min`: the triangle step runs only when at least that many lanes have a triangle waiting,
+// or when some lane cannot make progress without it -- triangle tests are then executed by
+// fuller warps (speculative while-while, Aila & Laine 2009).
+template <uint32_t E, int S, bool COUNT>
+TRT_DEV bool closest_round(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ClosestRay& s, uint32_t base,
+                           uint2* spill, WideCounts* wc, int tri_min) {
+    const uint32_t ttop = base + (S - 1) * E;
+    const float limit = s.d_min * kCullSlack;
+    // at least four free entries (a node step can push that many); tp - np = (free - 1) * E, signed:
+    // a completely full stack gives -E
+    const bool room = (int)(s.tp - s.np) >= (int)(3 * E);
+    {
+        const bool has_tri = s.tp != ttop;
+        const bool node_work = s.cur != kWideEmptyRef || s.np != base || s.nspill > 0;
+        const unsigned m_tri = __ballot_sync(0xffffffffu, has_tri);
+        const unsigned m_urgent = __ballot_sync(0xffffffffu, has_tri && (!room || !node_work));
+        if (__popc(m_tri) < tri_min && m_urgent == 0) tri_min = -1;  // skip the triangle step this round
+    }
+    // ---- choose this round's node: the held one, else the nearest-first stack --------------
+    int node = kWideEmptyRef;
+    if (room) {
+        node = s.cur;
+        s.cur = kWideEmptyRef;
+        if (node == kWideEmptyRef) {
+            while (s.np != base) {
+                s.np -= E;
+                const uint2 e = lds64(s.np);
+                if (__uint_as_float(e.x) < limit) { node = (int)e.y; break; }
+            }
+            if (node == kWideEmptyRef && s.nspill > 0) {  // deep trees only
+                while (s.nspill > 0) {
+                    const uint2 e = spill[--s.nspill];
+                    if (__uint_as_float(e.x) < limit) { node = (int)e.y; break; }
+                }
+            }
+        }
+    } else if (s.tp == ttop) {
+        // node stack full and no triangle to drain: move it to the local overflow (rare)
+#pragma unroll 1
+        for (uint32_t a = base; a != s.np; a += E) spill[s.nspill++] = lds64(a);
+        s.np = base;
+    }
+    // ---- choose this round's triangle -------------------------------------------------------
+    int tri = -1;
+    while (tri_min >= 0 && s.tp != ttop) {
+        const uint32_t top = s.tp + E;
+        const uint2 e = lds64(top);
+        if (!(__uint_as_float(e.x) < limit)) { s.tp = top; continue; }
+        const int code = (int)e.y;
+        tri = code >> 2;
+        const bool more = (code & 3) != 0;
+        sts64_if(more, top, e.x, (uint32_t)(code + 3));  // first + 1, count - 1
+        if (!more) s.tp = top;
+        break;
+    }
+    // ---- node step ----------------------------------------------------------------------------
+    if (node != kWideEmptyRef) {
+        if (COUNT) wc->nodes++;
+        NodeData n;
+        load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+        float t[4];
+        bool h[4];
+        h[0] = child_interval(n.nx.x, n.fx.x, n.ny.x, n.fy.x, n.nz.x, n.fz.x, s.o, s.inv, 0.f, limit, &t[0]);
+        h[1] = child_interval(n.nx.y, n.fx.y, n.ny.y, n.fy.y, n.nz.y, n.fz.y, s.o, s.inv, 0.f, limit, &t[1]);
+        h[2] = child_interval(n.nx.z, n.fx.z, n.ny.z, n.fy.z, n.nz.z, n.fz.z, s.o, s.inv, 0.f, limit, &t[2]);
+        h[3] = child_interval(n.nx.w, n.fx.w, n.ny.w, n.fy.w, n.nz.w, n.fz.w, s.o, s.inv, 0.f, limit, &t[3]);
+        const int r[4] = {n.ch.x, n.ch.y, n.ch.z, n.ch.w};
+        // nearest inner child stays in a register: entry distances are >= 0, so their bit
+        // patterns order like the floats; the child slot rides in the two low mantissa bits
+        unsigned key[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            key[k] = (h[k] && r[k] >= 0) ? ((__float_as_uint(t[k]) & ~3u) | (unsigned)k) : 0xffffffffu;
+        const unsigned best = min(min(key[0], key[1]), min(key[2], key[3]));
+        const int r01 = (best & 1u) ? r[1] : r[0], r23 = (best & 1u) ? r[3] : r[2];
+        const int rb = (best & 2u) ? r23 : r01;
+        s.cur = best != 0xffffffffu ? rb : kWideEmptyRef;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool leaf = r[k] < 0;
+            const bool push_tri = h[k] && leaf;
+            const bool push_node = h[k] && !leaf && key[k] != best;
+            const uint32_t tb = __float_as_uint(t[k]);
+            sts64_if(push_tri, s.tp, tb, (uint32_t)(~r[k]));
+            sts64_if(push_node, s.np, tb, (uint32_t)r[k]);
+            s.tp -= push_tri ? E : 0u;
+            s.np += push_node ? E : 0u;
+        }
+    }
+    // ---- triangle step ------------------------------------------------------------------------
+    if (tri >= 0) {
+        if (COUNT) wc->tris++;
+        const float4* tp = sc.tris + (size_t)tri * 3;
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+        const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
+        const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
+        const int code = f2i(ta.w);
+        const int tid = code & kTriIdMask;
+        if (t > 0.f && (t < s.d_min || (t == s.d_min && tid < s.id))) {
+            // would the reference traversal have reached this triangle?
+            float4 bmin, bmax;
+            derive_leaf_box(v0, v1, v2, &bmin, &bmax);
+            float entry;
+            if (code & kTriNoDerive) {
+                s.amb = true;
+            } else if (leaf_box_reach(bmin, bmax, s.o, s.inv, s.nxo != 0, s.nyo != 32, s.nzo != 64, &entry)) {
+                if (entry < t) { s.d_min = t; s.id = tid; }
+                else s.amb = true;  // reach depends on the reference's visit order: replay
+            }
+        }
+    }
+    return s.cur == kWideEmptyRef && s.np == base && s.tp == ttop && s.nspill == 0;  // done
+}
+
+// ---- any hit -----------------------------------------------------------------------------------
+struct ShadowRay {
+    F3 o, d, inv;
+    float max_dist, t_hi;
+    int nxo, nyo, nzo;
+    uint32_t np, tp;
+    int nspill;
+    bool occluded;
+};
+
+// Stack entries are 32-bit references here (no distances: the interval is fixed); the root is
+// pushed at begin.
+TRT_DEV void shadow_begin(ShadowRay& s, const float4 o4, const float4 d4, uint32_t base, uint32_t ttop, uint32_t E) {
+    s.o = f3(o4.x, o4.y, o4.z);
+    s.d = f3(d4.x, d4.y, d4.z);
+    s.inv = f3(p_rcp(s.d.x), p_rcp(s.d.y), p_rcp(s.d.z));  // raw reciprocal, reference :276
+    s.nxo = s.inv.x < 0.f ? 16 : 0;
+    s.nyo = s.inv.y < 0.f ? 48 : 32;
+    s.nzo = s.inv.z < 0.f ? 80 : 64;
+    s.max_dist = o4.w;
+    s.t_hi = p_sub(o4.w, 0.001f);
+    s.occluded = false;
+    sts32_if(true, base, 0u);  // root
+    s.np = base + E;
+    s.tp = ttop;
+    s.nspill = 0;
+}
+
+template <uint32_t E, int S, bool COUNT>
+TRT_DEV bool shadow_round(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ShadowRay& s, uint32_t base,
+                          uint32_t* spill, WideCounts* wc) {
+    const uint32_t ttop = base + (S - 1) * E;
+    int node = kWideEmptyRef;
+    if ((int)(s.tp - s.np) >= (int)(3 * E)) {
+        if (s.np != base) {
+            s.np -= E;
+            node = (int)lds32(s.np);
+        } else if (s.nspill > 0) {
+            node = (int)spill[--s.nspill];
+        }
+    } else if (s.tp == ttop) {
+#pragma unroll 1
+        for (uint32_t a = base; a != s.np; a += E) spill[s.nspill++] = lds32(a);
+        s.np = base;
+    }
+    int tri = -1;
+    if (s.tp != ttop) {
+        const uint32_t top = s.tp + E;
+        const int code = (int)lds32(top);
+        tri = code >> 2;
+        const bool more = (code & 3) != 0;
+        sts32_if(more, top, (uint32_t)(code + 3));
+        if (!more) s.tp = top;
+    }
+    if (node != kWideEmptyRef) {
+        if (COUNT) wc->nodes++;
+        NodeData n;
+        load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+        float t;
+        bool h[4];
+        // the reference's box interval for shadow rays is (0.001, max_dist)
+        h[0] = child_interval(n.nx.x, n.fx.x, n.ny.x, n.fy.x, n.nz.x, n.fz.x, s.o, s.inv, 0.001f, s.max_dist, &t);
+        h[1] = child_interval(n.nx.y, n.fx.y, n.ny.y, n.fy.y, n.nz.y, n.fz.y, s.o, s.inv, 0.001f, s.max_dist, &t);
+        h[2] = child_interval(n.nx.z, n.fx.z, n.ny.z, n.fy.z, n.nz.z, n.fz.z, s.o, s.inv, 0.001f, s.max_dist, &t);
+        h[3] = child_interval(n.nx.w, n.fx.w, n.ny.w, n.fy.w, n.nz.w, n.fz.w, s.o, s.inv, 0.001f, s.max_dist, &t);
+        const int r[4] = {n.ch.x, n.ch.y, n.ch.z, n.ch.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const bool leaf = r[k] < 0;
+            const bool push_tri = h[k] && leaf;
+            const bool push_node = h[k] && !leaf;
+            sts32_if(push_tri, s.tp, (uint32_t)(~r[k]));
+            sts32_if(push_node, s.np, (uint32_t)r[k]);
+            s.tp -= push_tri ? E : 0u;
+            s.np += push_node ? E : 0u;
+        }
+    }
+    if (tri >= 0) {
+        if (COUNT) wc->tris++;
+        const float4* tp = sc.tris + (size_t)tri * 3;
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+        const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
+        const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
+        if (t > 0.001f && t < s.t_hi) {
+            const int code = f2i(ta.w);
+            bool reach;
+            if (code & kTriNoDerive) {
+                // leaf box not derivable: ask the reference traversal itself (exact, rare)
+                Ray r;
+                r.o = s.o;
+                r.d = s.d;
+                VisitCounts vc = {0, 0, 0};
+                reach = ref_shadow<false>(sc, r, s.max_dist, &vc);
+            } else {
+                float4 bmin, bmax;
+                derive_leaf_box(v0, v1, v2, &bmin, &bmax);
+                reach = ref_slab(bmin, bmax, s.o, s.inv, 0.001f, s.max_dist);
+            }
+            if (reach) s.occluded = true;
+        }
+    }
+    return s.occluded || (s.np == base && s.tp == ttop && s.nspill == 0);  // done
+}
+
+}  // namespace trt

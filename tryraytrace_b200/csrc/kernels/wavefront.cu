@@ -6,8 +6,8 @@
 #include "wavefront.cuh"
 #include "raygen.cuh"
 #include "shade.cuh"
+#include "traverse_fast.cuh"
 #include "traverse_ref.cuh"
-#include "traverse_wide.cuh"
 #include "trt_capi.h"
 
 namespace trt {
@@ -52,15 +52,10 @@ __global__ void k_prepare(Control* ctl) {
     ctl->next_sample += (unsigned long long)n_regen;
     ctl->alive += n_regen - n_free;
     ctl->cnt_samples += (unsigned long long)n_regen;
-    ctl->cnt_closest += (unsigned long long)n_regen;
-    ctl->cnt_shadow += (unsigned long long)ctl->n_shadow;
     ctl->cnt_iterations += 1;
     ctl->n_free = 0;
-    ctl->n_shadow = 0;
-    ctl->n_replay = 0;
     ctl->cursor_extend = 0;
     ctl->cursor_shadow = 0;
-    ctl->cursor_replay = 0;
 }
 
 __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity) {
@@ -81,11 +76,18 @@ __global__ void k_reset_counters(Control* ctl) {
     ctl->cnt_nodes_closest = ctl->cnt_tris_closest = 0;
 }
 
+__global__ void k_reset_cursors(Control* ctl) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->cursor_extend = 0;
+    ctl->cursor_shadow = 0;
+}
+
 __global__ void k_init_pool(PoolView pool, int* free_list) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool.capacity) return;
     pool.ray_d[i] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
-    free_list[i] = i;
+    pool.sh_d[i] = make_float4(0.f, 0.f, 0.f, i2f(0));
+    if (free_list) free_list[i] = i;
 }
 
 // ---- XORWOW column table: col_vecs[f*w + col] = M^col * v0(frame f) --------------------
@@ -150,10 +152,16 @@ __global__ void __launch_bounds__(kBlock) k_regen(PoolView pool, const int* __re
     }
 }
 
-// ---- extend: closest hit for every active slot -----------------------------------------
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_extend(PoolView pool, SceneDev sc, Control* ctl, int* replay_list) {
-    unsigned long long nodes = 0, tris = 0;
+// warp-aggregated add of per-thread counters (one atomic per warp)
+TRT_DEV void warp_add(unsigned long long* counter, unsigned v) {
+    const unsigned total = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31u) == 0 && total) atomicAdd(counter, (unsigned long long)total);
+}
+
+// ---- extend, reference order: closest hit for every active slot --------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev sc, Control* ctl) {
+    unsigned nodes = 0, tris = 0, rays = 0;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pool.capacity; slot += gridDim.x * blockDim.x) {
         const float4 d4 = pool.ray_d[slot];
         if ((f2i(d4.w) & 0xff) != SLOT_ACTIVE) continue;
@@ -162,53 +170,45 @@ __global__ void __launch_bounds__(kBlock) k_extend(PoolView pool, SceneDev sc, C
         r.o = f3(o4.x, o4.y, o4.z);
         r.d = f3(d4.x, d4.y, d4.z);
         float t;
-        int id;
-        if (MODE == TRT_TRAVERSE_REF) {
-            VisitCounts vc = {0, 0, 0};
-            id = ref_closest<COUNT>(sc, r, &t, &vc);
-            if (COUNT) { nodes += vc.fetched; tris += vc.tris; }
-        } else {
-            WideCounts wc = {0, 0};
-            bool ambiguous;
-            id = wide_closest<COUNT>(sc, r, &t, &ambiguous, &wc);
-            if (COUNT) { nodes += wc.nodes; tris += wc.tris; }
-            if (ambiguous) {  // rare: re-run in reference order
-                VisitCounts vc = {0, 0, 0};
-                id = ref_closest<COUNT>(sc, r, &t, &vc);
-                if (COUNT) { nodes += vc.fetched; tris += vc.tris; }
-                atomicAdd(&ctl->cnt_replays, 1ull);
-            }
-        }
+        VisitCounts vc = {0, 0, 0};
+        const int id = ref_closest<COUNT>(sc, r, &t, &vc);
+        if (COUNT) { nodes += vc.fetched; tris += vc.tris; }
+        rays++;
         pool.hit[slot] = make_float2(t, i2f(id));
     }
+    warp_add(&ctl->cnt_closest, rays);
     if (COUNT) {
-        atomicAdd(&ctl->cnt_nodes, nodes);
-        atomicAdd(&ctl->cnt_tris, tris);
-        atomicAdd(&ctl->cnt_nodes_closest, nodes);
-        atomicAdd(&ctl->cnt_tris_closest, tris);
+        warp_add(&ctl->cnt_nodes, nodes);
+        warp_add(&ctl->cnt_tris, tris);
+        warp_add(&ctl->cnt_nodes_closest, nodes);
+        warp_add(&ctl->cnt_tris_closest, tris);
     }
-    (void)replay_list;
 }
 
 // ---- shade: one thread per slot --------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, ShadowView sq, int* __restrict__ free_list,
-                                                  Control* ctl, SceneDev sc, JobParams job) {
+__global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict__ free_list, Control* ctl,
+                                                  SceneDev sc, JobParams job) {
     __shared__ int scratch[2 + kBlock / 32];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of kBlock
     const float4 d4 = pool.ray_d[slot];
     const int flags = f2i(d4.w);
     const int state = flags & 0xff;
-    bool terminated = false, cont = false;
-    PathVertexIO io;
-    io.shadow = false;
-    int pix = 0;
+    bool terminated = false;
     if (state != SLOT_DEAD) {
+        PathVertexIO io;
+        io.shadow = false;
         const float4 thr4 = pool.thr[slot];
         const float4 rad4 = pool.rad[slot];
-        pix = f2i(thr4.w);
+        const int pix = f2i(thr4.w);
         io.thr = f3(thr4.x, thr4.y, thr4.z);
         io.rad = f3(rad4.x, rad4.y, rad4.z);
+        io.depth = (flags >> 8) & 0xff;
+        if (io.depth > 0) {
+            // next-event estimate of the previous vertex; the shadow kernel zeroed it if occluded
+            const float4 p = pool.pend[slot];
+            io.rad = v_add(io.rad, f3(p.x, p.y, p.z));
+        }
         if (state == SLOT_ACTIVE) {
             const float2 hit = pool.hit[slot];
             const int id = f2i(hit.y);
@@ -220,7 +220,6 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, ShadowView sq, 
                 const uint2 rb = pool.rng_b[slot];
                 io.ray.o = f3(o4.x, o4.y, o4.z);
                 io.ray.d = f3(d4.x, d4.y, d4.z);
-                io.depth = (flags >> 8) & 0xff;
                 io.prev_mode = (flags >> 16) & 0xff;
                 io.rng.v0 = ra.x; io.rng.v1 = ra.y; io.rng.v2 = ra.z; io.rng.v3 = ra.w;
                 io.rng.v4 = rb.x; io.rng.d = rb.y;
@@ -231,7 +230,6 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, ShadowView sq, 
                     // the reference loop ends after max_depth vertices; a path that still has a
                     // shadow ray in flight is finalised one iteration later (SLOT_FINISH)
                     const int ns = depth >= job.rc.max_depth ? SLOT_FINISH : SLOT_ACTIVE;
-                    cont = ns == SLOT_ACTIVE;
                     pool.ray_o[slot] = make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, 0.f);
                     pool.ray_d[slot] = make_float4(io.ray.d.x, io.ray.d.y, io.ray.d.z,
                                                    i2f(pack_flags(ns, depth, io.prev_mode)));
@@ -239,6 +237,15 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, ShadowView sq, 
                     pool.rad[slot] = make_float4(io.rad.x, io.rad.y, io.rad.z, 0.f);
                     pool.rng_a[slot] = make_uint4(io.rng.v0, io.rng.v1, io.rng.v2, io.rng.v3);
                     pool.rng_b[slot] = make_uint2(io.rng.v4, io.rng.d);
+                    if (io.shadow) {
+                        pool.pend[slot] = make_float4(io.shadow_contrib.x, io.shadow_contrib.y, io.shadow_contrib.z, 0.f);
+                        pool.sh_o[slot] = make_float4(io.shadow_ray.o.x, io.shadow_ray.o.y, io.shadow_ray.o.z,
+                                                      io.shadow_max_dist);
+                        pool.sh_d[slot] = make_float4(io.shadow_ray.d.x, io.shadow_ray.d.y, io.shadow_ray.d.z, i2f(1));
+                    } else {
+                        pool.pend[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        pool.sh_d[slot] = make_float4(0.f, 0.f, 0.f, i2f(0));
+                    }
                 }
             }
         } else {
@@ -253,201 +260,340 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, ShadowView sq, 
                 atomicAdd(a + 2, rad.z);
             }
             pool.ray_d[slot] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
+            pool.sh_d[slot] = make_float4(0.f, 0.f, 0.f, i2f(0));
         }
     }
     const int fi = block_append(terminated, &ctl->n_free, scratch);
     if (terminated) free_list[fi] = slot;
-    const int si = block_append(io.shadow, &ctl->n_shadow, scratch);
-    if (io.shadow) {
-        sq.o[si] = make_float4(io.shadow_ray.o.x, io.shadow_ray.o.y, io.shadow_ray.o.z, io.shadow_max_dist);
-        sq.d[si] = make_float4(io.shadow_ray.d.x, io.shadow_ray.d.y, io.shadow_ray.d.z, i2f(slot));
-        sq.c[si] = make_float4(io.shadow_contrib.x, io.shadow_contrib.y, io.shadow_contrib.z, 0.f);
-    }
-    // closest-hit rays issued for the next iteration (ray statistics are always maintained)
-    const int n_cont = __syncthreads_count(cont);
-    if (threadIdx.x == 0 && n_cont) atomicAdd(&ctl->cnt_closest, (unsigned long long)n_cont);
 }
 
-// ---- shadow: any hit for every queued shadow ray ----------------------------------------
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_shadow(PoolView pool, ShadowView sq, SceneDev sc, Control* ctl) {
-    const int n = ctl->n_shadow;
-    unsigned long long nodes = 0, tris = 0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const float4 o4 = sq.o[j], d4 = sq.d[j];
+// ---- shadow, reference order: any hit for every slot that holds a shadow ray ---------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_shadow_ref(PoolView pool, SceneDev sc, Control* ctl) {
+    unsigned nodes = 0, tris = 0, rays = 0;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pool.capacity; slot += gridDim.x * blockDim.x) {
+        const float4 d4 = pool.sh_d[slot];
+        if (f2i(d4.w) != 1) continue;
+        const float4 o4 = pool.sh_o[slot];
         Ray r;
         r.o = f3(o4.x, o4.y, o4.z);
         r.d = f3(d4.x, d4.y, d4.z);
-        bool occluded;
-        if (MODE == TRT_TRAVERSE_REF) {
-            VisitCounts vc = {0, 0, 0};
-            occluded = ref_shadow<COUNT>(sc, r, o4.w, &vc);
-            if (COUNT) { nodes += vc.fetched; tris += vc.tris; }
-        } else {
-            WideCounts wc = {0, 0};
-            occluded = wide_shadow<COUNT>(sc, r, o4.w, &wc);
-            if (COUNT) { nodes += wc.nodes; tris += wc.tris; }
-        }
-        if (!occluded) {
-            const int slot = f2i(d4.w);
-            const float4 c = sq.c[j];
-            float4 rad = pool.rad[slot];  // one shadow ray per slot per iteration: no race
-            rad.x += c.x; rad.y += c.y; rad.z += c.z;
-            pool.rad[slot] = rad;
-        }
+        VisitCounts vc = {0, 0, 0};
+        const bool occluded = ref_shadow<COUNT>(sc, r, o4.w, &vc);
+        if (COUNT) { nodes += vc.fetched; tris += vc.tris; }
+        rays++;
+        if (occluded) pool.pend[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    warp_add(&ctl->cnt_shadow, rays);
     if (COUNT) {
-        atomicAdd(&ctl->cnt_nodes, nodes);
-        atomicAdd(&ctl->cnt_tris, tris);
+        warp_add(&ctl->cnt_nodes, nodes);
+        warp_add(&ctl->cnt_tris, tris);
     }
 }
 
-
 // ---- persistent fast-path kernels: while-while traversal with dynamic ray fetch -------------
-// One warp holds 32 rays.  Rounds (traverse_wide.cuh) keep the lanes converged; a lane whose
-// ray has finished writes its result and goes idle; when a quarter of the warp is idle the
-// idle lanes grab the next slots from a global cursor with one warp-aggregated atomic
-// (__ballot_sync + __popc) and continue -- so a long ray never holds 31 finished lanes hostage.
-constexpr int kFastBlock = 128;
-constexpr int kRefillBelow = 25;  // refill when fewer than this many lanes hold a ray
+// One CTA per SM.  Shared memory, in order:
+//   [ top-of-tree nodes: k_smem x 128 B ][ per-thread stacks: S x THREADS entries ]
+//   [ per-warp ray staging: 2 buffers x (32 origins + 32 directions) x 16 B ][ per-warp mbarriers ]
+// A warp holds 32 rays.  Rounds (traverse_fast.cuh) keep the lanes converged; a lane whose ray has
+// finished writes its result and goes idle; when fewer than `refill_below` lanes hold a ray the
+// idle lanes take the next rays from the warp's staging buffer.  The buffer is refilled a chunk
+// (32 consecutive slots) at a time: lane 0 claims the chunk with one atomicAdd on a global
+// cursor and issues two TMA bulk copies (origins, directions) that complete on an mbarrier; the
+// copy for chunk r+1 is in flight while chunk r is being traced.
+constexpr int kChunk = 32;
+constexpr int kStageBytesPerWarp = 2 * 2 * kChunk * 16;  // 2 buffers x (o + d) x 32 x float4
 
-template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_extend_fast(PoolView pool, SceneDev sc, Control* ctl) {
-    const unsigned lane = threadIdx.x & 31u;
+template <int THREADS> struct FastCfg;
+template <> struct FastCfg<512>  { static constexpr int SC = 16, SS = 16; };
+template <> struct FastCfg<768>  { static constexpr int SC = 12, SS = 12; };
+template <> struct FastCfg<1024> { static constexpr int SC = 8,  SS = 10; };
+
+struct Feeder {  // warp-uniform state of the staging double buffer
+    int cur_buf, cur_pos, cur_base, nxt_base;
+    bool nxt_req, drained;
+    unsigned phase;  // bit b = parity the next wait on buffer b uses
+};
+
+TRT_DEV void feeder_init(Feeder& f) {
+    f.cur_buf = 0;
+    f.cur_pos = kChunk;
+    f.cur_base = 0;
+    f.nxt_base = 0;
+    f.nxt_req = false;
+    f.drained = false;
+    f.phase = 0;
+}
+TRT_DEV bool feeder_exhausted(const Feeder& f) { return f.drained && f.cur_pos >= kChunk && !f.nxt_req; }
+
+// Advance the double buffer: swap in the prefetched chunk when the current one is used up, and
+// request the chunk after it.  `block` = nobody in the warp has work, so waiting is all there is
+// to do.  Returns with f.cur_pos < kChunk when rays can be handed out.
+TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const float4* src_o, const float4* src_d,
+                            int* cursor, int limit, unsigned lane, bool block) {
+    if (f.cur_pos >= kChunk && f.nxt_req) {
+        const int nb = f.cur_buf ^ 1;
+        const uint32_t parity = (f.phase >> nb) & 1u;
+        int ready = 0;
+        if (lane == 0) {
+            ready = mbar_try_wait(&bars[nb], parity) ? 1 : 0;
+            if (block) {
+                while (!ready) ready = mbar_try_wait(&bars[nb], parity) ? 1 : 0;
+            }
+        }
+        ready = __shfl_sync(0xffffffffu, ready, 0);
+        if (ready) {
+            f.phase ^= 1u << nb;
+            f.cur_buf = nb;
+            f.cur_pos = 0;
+            f.cur_base = f.nxt_base;
+            f.nxt_req = false;
+        }
+    }
+    if (!f.nxt_req && !f.drained) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, kChunk);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= limit) {
+            f.drained = true;
+        } else {
+            const int nb = f.cur_buf ^ 1;  // the buffer not being read
+            if (lane == 0) {
+                float4* dst = stage + nb * (2 * kChunk);
+                mbar_expect_tx(&bars[nb], 2 * kChunk * 16);
+                bulk_g2s(dst, src_o + base, kChunk * 16, &bars[nb]);
+                bulk_g2s(dst + kChunk, src_d + base, kChunk * 16, &bars[nb]);
+            }
+            f.nxt_req = true;
+            f.nxt_base = base;
+        }
+    }
+}
+
+template <int THREADS, bool COUNT>
+__global__ void __launch_bounds__(THREADS, 1)
+k_extend_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_below, int tri_min, int* amb_out) {
+    constexpr int S = FastCfg<THREADS>::SC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_nodes = smem;
+    uint2* s_stack = reinterpret_cast<uint2*>(smem + (size_t)k_smem * 128);
+    float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) +
+                                                   (THREADS / 32) * kStageBytesPerWarp);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    ClosestState st;
-    ClosestStack stack;
-    st.nsp = 0;
-    st.tsp = 0;
+    for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
+        reinterpret_cast<float4*>(s_nodes)[i] = __ldg(sc.wide_nodes + i);
+    if (lane == 0) {
+        mbar_init(&s_bars[warp * 2], 1);
+        mbar_init(&s_bars[warp * 2 + 1], 1);
+    }
+    mbar_fence_init();
+    __syncthreads();
+
+    float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
+    uint64_t* bars = s_bars + warp * 2;
+    constexpr uint32_t E = THREADS * 8;  // bytes between consecutive stack entries of one lane
+    const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
+    const uint32_t stk_ttop = stk_base + (S - 1) * E;
+    uint2 spill[kSpillEntries];
+    Feeder fd;
+    feeder_init(fd);
+    ClosestRay st;
+    st.np = stk_base;
+    st.tp = stk_ttop;
+    st.nspill = 0;
     st.cur = kWideEmptyRef;
     WideCounts wc = {0, 0};
     bool has = false;
-    bool drained = false;  // warp-uniform: the cursor ran past the pool
     int slot = -1;
-    unsigned replays = 0;
+    unsigned replays = 0, rays = 0;
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
-        if (!drained && __popc(act) < kRefillBelow) {
-            const unsigned idle = ~act;
-            const int n = __popc(idle);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&ctl->cursor_extend, n);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!has) {
-                const int my = base + __popc(idle & lt_mask);
-                if (my < pool.capacity) {
-                    const float4 d4 = pool.ray_d[my];
+        if (__popc(act) < refill_below && !feeder_exhausted(fd)) {
+            feeder_advance(fd, stage, bars, pool.ray_o, pool.ray_d, &ctl->cursor_extend, pool.capacity, lane, act == 0);
+            if (fd.cur_pos < kChunk) {
+                const unsigned idle = ~act;
+                const int my = fd.cur_pos + __popc(idle & lt_mask);
+                if (!has && my < kChunk) {
+                    const float4* buf = stage + fd.cur_buf * (2 * kChunk);
+                    const float4 d4 = buf[kChunk + my];
                     if ((f2i(d4.w) & 0xff) == SLOT_ACTIVE) {
-                        const float4 o4 = pool.ray_o[my];
-                        Ray r;
-                        r.o = f3(o4.x, o4.y, o4.z);
-                        r.d = f3(d4.x, d4.y, d4.z);
-                        closest_begin(st, r);
+                        closest_begin(st, buf[my], d4, stk_base, stk_ttop);
                         has = true;
-                        slot = my;
+                        slot = fd.cur_base + my;
+                        rays++;
                     }
                 }
+                fd.cur_pos = min(kChunk, fd.cur_pos + __popc(idle));
+                act = __ballot_sync(0xffffffffu, has);
             }
-            drained = base + n >= pool.capacity;
-            act = __ballot_sync(0xffffffffu, has);
         }
         if (act == 0) {
-            if (drained) break;
+            if (feeder_exhausted(fd)) break;
             continue;
         }
-        if (has) {
-            closest_round<COUNT>(sc, st, stack, &wc);
-            if (closest_done(st)) {
-                float t = st.d_min;
-                int id = st.id;
-                if (st.amb) {  // rare: order-dependent reach, re-run in reference order
-                    Ray r;
-                    r.o = st.o;
-                    r.d = st.d;
-                    VisitCounts vc = {0, 0, 0};
-                    id = ref_closest<false>(sc, r, &t, &vc);
-                    replays++;
-                }
-                pool.hit[slot] = make_float2(t, i2f(id));
-                has = false;
+        // every lane takes part in the round (warp votes inside); a lane without a ray has empty stacks
+        if (closest_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc, tri_min) && has) {
+            float t = st.d_min;
+            int id = st.id;
+            if (st.amb) {  // rare: order-dependent reach, re-run in reference order
+                Ray r;
+                r.o = st.o;
+                r.d = st.d;
+                VisitCounts vc = {0, 0, 0};
+                id = ref_closest<false>(sc, r, &t, &vc);
+                replays++;
             }
+            st_cs_f2(&pool.hit[slot], make_float2(t, i2f(id)));
+            if (amb_out) amb_out[slot] = st.amb ? 1 : 0;
+            has = false;
         }
     }
+    warp_add(&ctl->cnt_closest, rays);
     if (COUNT) {
-        atomicAdd(&ctl->cnt_nodes, (unsigned long long)wc.nodes);
-        atomicAdd(&ctl->cnt_tris, (unsigned long long)wc.tris);
-        atomicAdd(&ctl->cnt_nodes_closest, (unsigned long long)wc.nodes);
-        atomicAdd(&ctl->cnt_tris_closest, (unsigned long long)wc.tris);
+        warp_add(&ctl->cnt_nodes, wc.nodes);
+        warp_add(&ctl->cnt_tris, wc.tris);
+        warp_add(&ctl->cnt_nodes_closest, wc.nodes);
+        warp_add(&ctl->cnt_tris_closest, wc.tris);
     }
-    if (replays) atomicAdd(&ctl->cnt_replays, (unsigned long long)replays);
+    warp_add(&ctl->cnt_replays, replays);
 }
 
-template <bool COUNT, int MINB>
-__global__ void __launch_bounds__(kFastBlock, MINB) k_shadow_fast(PoolView pool, ShadowView sq, SceneDev sc, Control* ctl) {
-    const unsigned lane = threadIdx.x & 31u;
+template <int THREADS, bool COUNT>
+__global__ void __launch_bounds__(THREADS, 1)
+k_shadow_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_below) {
+    constexpr int S = FastCfg<THREADS>::SS;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_nodes = smem;
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem + (size_t)k_smem * 128);
+    float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) +
+                                                   (THREADS / 32) * kStageBytesPerWarp);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const int n_rays = ctl->n_shadow;
-    ShadowState st;
-    ShadowStack stack;
-    st.nsp = 0;
-    st.tsp = 0;
+    for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
+        reinterpret_cast<float4*>(s_nodes)[i] = __ldg(sc.wide_nodes + i);
+    if (lane == 0) {
+        mbar_init(&s_bars[warp * 2], 1);
+        mbar_init(&s_bars[warp * 2 + 1], 1);
+    }
+    mbar_fence_init();
+    __syncthreads();
+
+    float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
+    uint64_t* bars = s_bars + warp * 2;
+    constexpr uint32_t E = THREADS * 4;
+    const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
+    const uint32_t stk_ttop = stk_base + (S - 1) * E;
+    uint32_t spill[kSpillEntries];
+    Feeder fd;
+    feeder_init(fd);
+    ShadowRay st;
+    st.np = stk_base;
+    st.tp = stk_ttop;
+    st.nspill = 0;
     st.occluded = false;
     WideCounts wc = {0, 0};
     bool has = false;
-    bool drained = false;
-    int entry = -1;
+    int slot = -1;
+    unsigned rays = 0;
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
-        if (!drained && __popc(act) < kRefillBelow) {
-            const unsigned idle = ~act;
-            const int n = __popc(idle);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&ctl->cursor_shadow, n);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!has) {
-                const int my = base + __popc(idle & lt_mask);
-                if (my < n_rays) {
-                    const float4 o4 = sq.o[my], d4 = sq.d[my];
-                    Ray r;
-                    r.o = f3(o4.x, o4.y, o4.z);
-                    r.d = f3(d4.x, d4.y, d4.z);
-                    shadow_begin(st, stack, r, o4.w);
-                    has = true;
-                    entry = my;
+        if (__popc(act) < refill_below && !feeder_exhausted(fd)) {
+            feeder_advance(fd, stage, bars, pool.sh_o, pool.sh_d, &ctl->cursor_shadow, pool.capacity, lane, act == 0);
+            if (fd.cur_pos < kChunk) {
+                const unsigned idle = ~act;
+                const int my = fd.cur_pos + __popc(idle & lt_mask);
+                if (!has && my < kChunk) {
+                    const float4* buf = stage + fd.cur_buf * (2 * kChunk);
+                    const float4 d4 = buf[kChunk + my];
+                    if (f2i(d4.w) == 1) {
+                        shadow_begin(st, buf[my], d4, stk_base, stk_ttop, E);
+                        has = true;
+                        slot = fd.cur_base + my;
+                        rays++;
+                    }
                 }
+                fd.cur_pos = min(kChunk, fd.cur_pos + __popc(idle));
+                act = __ballot_sync(0xffffffffu, has);
             }
-            drained = base + n >= n_rays;
-            act = __ballot_sync(0xffffffffu, has);
         }
         if (act == 0) {
-            if (drained) break;
+            if (feeder_exhausted(fd)) break;
             continue;
         }
         if (has) {
-            shadow_round<COUNT>(sc, st, stack, &wc);
-            if (shadow_done(st)) {
-                if (!st.occluded) {
-                    const int slot = f2i(sq.d[entry].w);
-                    const float4 c = sq.c[entry];
-                    float4 rad = pool.rad[slot];  // one shadow ray per slot per iteration: no race
-                    rad.x += c.x; rad.y += c.y; rad.z += c.z;
-                    pool.rad[slot] = rad;
-                }
+            if (shadow_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc)) {
+                // the next-event contribution waits in pend; an occluded ray cancels it
+                if (st.occluded) __stcs(&pool.pend[slot], make_float4(0.f, 0.f, 0.f, 0.f));
                 has = false;
             }
         }
     }
+    warp_add(&ctl->cnt_shadow, rays);
     if (COUNT) {
-        atomicAdd(&ctl->cnt_nodes, (unsigned long long)wc.nodes);
-        atomicAdd(&ctl->cnt_tris, (unsigned long long)wc.tris);
+        warp_add(&ctl->cnt_nodes, wc.nodes);
+        warp_add(&ctl->cnt_tris, wc.tris);
     }
 }
 
 // ---- parity / test entry points -------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_trace_primary(SceneDev sc, JobParams job, int* out_id, float* out_t,
-                                                          float* out_ray, uint32_t* out_fetched,
-                                                          uint32_t* out_entered, uint32_t* out_tris) {
+// primary rays of one frame into a scratch pool (slot = reference pixel index)
+__global__ void __launch_bounds__(kBlock) k_pack_primary(PoolView pool, JobParams job, float* out_ray) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= pool.capacity) return;
+    if (pix >= job.rc.width * job.rc.height) {
+        pool.ray_d[pix] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
+        return;
+    }
+    const int row = pix / job.rc.width, col = pix - row * job.rc.width;
+    const int y = job.rc.height - 1 - row;
+    Xorwow rng = sample_rng(job, 0, row, col);
+    const Ray r = primary_ray(job.cam, col, y, job.rc.width, job.rc.height, rng);
+    pool.ray_o[pix] = make_float4(r.o.x, r.o.y, r.o.z, 0.f);
+    pool.ray_d[pix] = make_float4(r.d.x, r.d.y, r.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
+    if (out_ray) {
+        float* p = out_ray + (size_t)pix * 6;
+        p[0] = r.o.x; p[1] = r.o.y; p[2] = r.o.z; p[3] = r.d.x; p[4] = r.d.y; p[5] = r.d.z;
+    }
+}
+
+// caller-provided rays (8 floats: o.xyz, d.xyz, t_max, unused) into a scratch pool, as closest-hit
+// rays and as shadow rays at once
+__global__ void __launch_bounds__(kBlock) k_pack_rays(PoolView pool, const float* __restrict__ rays, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pool.capacity) return;
+    if (i >= n) {
+        pool.ray_d[i] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
+        pool.sh_d[i] = make_float4(0.f, 0.f, 0.f, i2f(0));
+        return;
+    }
+    const float* p = rays + (size_t)i * 8;
+    pool.ray_o[i] = make_float4(p[0], p[1], p[2], 0.f);
+    pool.ray_d[i] = make_float4(p[3], p[4], p[5], i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
+    pool.sh_o[i] = make_float4(p[0], p[1], p[2], p[6]);
+    pool.sh_d[i] = make_float4(p[3], p[4], p[5], i2f(1));
+    pool.pend[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_unpack_hits(PoolView pool, int n, int* out_id, float* out_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 h = pool.hit[i];
+    if (out_id) out_id[i] = f2i(h.y);
+    if (out_t) out_t[i] = h.x;
+}
+
+__global__ void __launch_bounds__(kBlock) k_unpack_occluded(PoolView pool, int n, int* out_occ) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out_occ[i] = pool.pend[i].x == 0.f ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kBlock) k_trace_primary_ref(SceneDev sc, JobParams job, int* out_id, float* out_t,
+                                                              float* out_ray, uint32_t* out_fetched,
+                                                              uint32_t* out_entered, uint32_t* out_tris) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= job.rc.width * job.rc.height) return;
     const int row = pix / job.rc.width, col = pix - row * job.rc.width;
@@ -455,22 +601,8 @@ __global__ void __launch_bounds__(kBlock) k_trace_primary(SceneDev sc, JobParams
     Xorwow rng = sample_rng(job, 0, row, col);
     const Ray r = primary_ray(job.cam, col, y, job.rc.width, job.rc.height, rng);
     float t;
-    int id;
     VisitCounts vc = {0, 0, 0};
-    if (MODE == TRT_TRAVERSE_REF) {
-        id = ref_closest<true>(sc, r, &t, &vc);
-    } else {
-        WideCounts wc = {0, 0};
-        bool ambiguous;
-        id = wide_closest<true>(sc, r, &t, &ambiguous, &wc);
-        vc.fetched = wc.nodes;
-        vc.tris = wc.tris;
-        vc.entered = ambiguous ? 1u : 0u;  // FAST mode reports "replayed" here
-        if (ambiguous) {
-            VisitCounts v2 = {0, 0, 0};
-            id = ref_closest<false>(sc, r, &t, &v2);
-        }
-    }
+    const int id = ref_closest<true>(sc, r, &t, &vc);
     if (out_id) out_id[pix] = id;
     if (out_t) out_t[pix] = t;
     if (out_ray) {
@@ -482,9 +614,8 @@ __global__ void __launch_bounds__(kBlock) k_trace_primary(SceneDev sc, JobParams
     if (out_tris) out_tris[pix] = vc.tris;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_trace_closest(SceneDev sc, const float* __restrict__ rays, int n,
-                                                          int* out_id, float* out_t) {
+__global__ void __launch_bounds__(kBlock) k_trace_closest_ref(SceneDev sc, const float* __restrict__ rays, int n,
+                                                              int* out_id, float* out_t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = rays + (size_t)i * 8;
@@ -492,41 +623,21 @@ __global__ void __launch_bounds__(kBlock) k_trace_closest(SceneDev sc, const flo
     r.o = f3(p[0], p[1], p[2]);
     r.d = f3(p[3], p[4], p[5]);
     float t;
-    int id;
-    if (MODE == TRT_TRAVERSE_REF) {
-        VisitCounts vc = {0, 0, 0};
-        id = ref_closest<false>(sc, r, &t, &vc);
-    } else {
-        WideCounts wc = {0, 0};
-        bool ambiguous;
-        id = wide_closest<false>(sc, r, &t, &ambiguous, &wc);
-        if (ambiguous) {
-            VisitCounts vc = {0, 0, 0};
-            id = ref_closest<false>(sc, r, &t, &vc);
-        }
-    }
-    out_id[i] = id;
+    VisitCounts vc = {0, 0, 0};
+    out_id[i] = ref_closest<false>(sc, r, &t, &vc);
     if (out_t) out_t[i] = t;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_trace_shadow(SceneDev sc, const float* __restrict__ rays, int n,
-                                                         int* out_occ) {
+__global__ void __launch_bounds__(kBlock) k_trace_shadow_ref(SceneDev sc, const float* __restrict__ rays, int n,
+                                                             int* out_occ) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = rays + (size_t)i * 8;
     Ray r;
     r.o = f3(p[0], p[1], p[2]);
     r.d = f3(p[3], p[4], p[5]);
-    bool occ;
-    if (MODE == TRT_TRAVERSE_REF) {
-        VisitCounts vc = {0, 0, 0};
-        occ = ref_shadow<false>(sc, r, p[6], &vc);
-    } else {
-        WideCounts wc = {0, 0};
-        occ = wide_shadow<false>(sc, r, p[6], &wc);
-    }
-    out_occ[i] = occ ? 1 : 0;
+    VisitCounts vc = {0, 0, 0};
+    out_occ[i] = ref_shadow<false>(sc, r, p[6], &vc) ? 1 : 0;
 }
 
 __global__ void k_rng_states(JobParams job, int f, int first_pixel, int n, uint32_t* out) {
@@ -556,9 +667,85 @@ __global__ void k_tonemap(const float4* __restrict__ accum, int n, float inv_fra
 
 int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
 
+template <int THREADS>
+size_t fast_smem_bytes(int k_smem, bool shadow) {
+    const size_t stack = shadow ? (size_t)FastCfg<THREADS>::SS * THREADS * 4 : (size_t)FastCfg<THREADS>::SC * THREADS * 8;
+    return (size_t)k_smem * 128 + stack + (size_t)(THREADS / 32) * (kStageBytesPerWarp + 16);
+}
+
+template <int THREADS, bool COUNT>
+void launch_extend_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims, int* amb_out,
+                        cudaStream_t s) {
+    const int k = min(dims.smem_nodes, sc.n_wide_nodes);
+    k_extend_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, false), s>>>(
+        pool, sc, ctl, k, dims.refill_below, dims.tri_min, amb_out);
+}
+template <int THREADS, bool COUNT>
+void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims,
+                        cudaStream_t s) {
+    const int k = min(dims.smem_nodes, sc.n_wide_nodes);
+    k_shadow_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, true), s>>>(pool, sc, ctl, k,
+                                                                                              dims.refill_below);
+}
+
+template <bool COUNT>
+void extend_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims, int* amb_out,
+                 cudaStream_t s) {
+    switch (dims.fast_threads) {
+    case 1024: launch_extend_fast<1024, COUNT>(pool, sc, ctl, dims, amb_out, s); break;
+    case 768: launch_extend_fast<768, COUNT>(pool, sc, ctl, dims, amb_out, s); break;
+    default: launch_extend_fast<512, COUNT>(pool, sc, ctl, dims, amb_out, s); break;
+    }
+}
+template <bool COUNT>
+void shadow_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
+    switch (dims.fast_threads) {
+    case 1024: launch_shadow_fast<1024, COUNT>(pool, sc, ctl, dims, s); break;
+    case 768: launch_shadow_fast<768, COUNT>(pool, sc, ctl, dims, s); break;
+    default: launch_shadow_fast<512, COUNT>(pool, sc, ctl, dims, s); break;
+    }
+}
+
+template <class K>
+int opt_in_smem(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess ? 0 : -1;
+}
+
 }  // namespace
 
 // ---- launchers -------------------------------------------------------------------------------
+int wf_configure() {
+    int rc = 0;
+    rc |= opt_in_smem(k_extend_fast<512, false>);
+    rc |= opt_in_smem(k_extend_fast<512, true>);
+    rc |= opt_in_smem(k_extend_fast<768, false>);
+    rc |= opt_in_smem(k_extend_fast<768, true>);
+    rc |= opt_in_smem(k_extend_fast<1024, false>);
+    rc |= opt_in_smem(k_extend_fast<1024, true>);
+    rc |= opt_in_smem(k_shadow_fast<512, false>);
+    rc |= opt_in_smem(k_shadow_fast<512, true>);
+    rc |= opt_in_smem(k_shadow_fast<768, false>);
+    rc |= opt_in_smem(k_shadow_fast<768, true>);
+    rc |= opt_in_smem(k_shadow_fast<1024, false>);
+    rc |= opt_in_smem(k_shadow_fast<1024, true>);
+    return rc;
+}
+
+size_t wf_fast_smem_bytes(int threads, int smem_nodes, bool shadow) {
+    switch (threads) {
+    case 512: return fast_smem_bytes<512>(smem_nodes, shadow);
+    case 768: return fast_smem_bytes<768>(smem_nodes, shadow);
+    case 1024: return fast_smem_bytes<1024>(smem_nodes, shadow);
+    default: return 0;
+    }
+}
+
+int wf_fast_max_smem_nodes(int threads, size_t smem_limit) {
+    const size_t fixed = wf_fast_smem_bytes(threads, 0, false);  // the closest-hit kernel has the larger stacks
+    if (fixed == 0 || fixed >= smem_limit) return 0;
+    return (int)((smem_limit - fixed) / 128);
+}
+
 void wf_init_pool(const PoolView& pool, int* free_list, Control* ctl, cudaStream_t s) {
     (void)ctl;
     k_init_pool<<<grid_for(pool.capacity), kBlock, 0, s>>>(pool, free_list);
@@ -580,9 +767,8 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
 int wf_kernels_per_iteration(int) { return 5; }
 
 template <int MODE, bool COUNT>
-static void iteration_impl(const PoolView& pool, const ShadowView& sq, int* free_list, int* replay_list, Control* ctl,
-                           const SceneDev& sc, const JobParams& job, const LaunchDims& dims, cudaStream_t s,
-                           cudaEvent_t* marks) {
+static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const JobParams& job,
+                           const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
     auto mark = [&](int i) { if (marks) cudaEventRecord(marks[i], s); };
@@ -590,78 +776,66 @@ static void iteration_impl(const PoolView& pool, const ShadowView& sq, int* free
     k_prepare<<<1, 32, 0, s>>>(ctl);
     k_regen<<<persistent < full ? persistent : full, kBlock, 0, s>>>(pool, free_list, ctl, job);
     mark(1);
-    if (MODE == TRT_TRAVERSE_FAST) {
-        // persistent grids: enough CTAs to fill every SM, each warp pulls rays until the queue is dry
-        const int fast_grid = dims.sms * dims.fast_blocks_per_sm;
-        switch (dims.fast_variant) {  // register budget of the persistent kernels (tuning knob)
-        case 4:
-            k_extend_fast<COUNT, 4><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
-            mark(2);
-            k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
-            mark(3);
-            k_shadow_fast<COUNT, 4><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
-            break;
-        case 6:
-            k_extend_fast<COUNT, 6><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
-            mark(2);
-            k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
-            mark(3);
-            k_shadow_fast<COUNT, 6><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
-            break;
-        default:
-            k_extend_fast<COUNT, 8><<<fast_grid, kFastBlock, 0, s>>>(pool, sc, ctl);
-            mark(2);
-            k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
-            mark(3);
-            k_shadow_fast<COUNT, 8><<<fast_grid, kFastBlock, 0, s>>>(pool, sq, sc, ctl);
-            break;
-        }
-    } else {
-        k_extend<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl, replay_list);
-        mark(2);
-        k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, sq, free_list, ctl, sc, job);
-        mark(3);
-        k_shadow<MODE, COUNT><<<full, kBlock, 0, s>>>(pool, sq, sc, ctl);
-    }
+    if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, ctl, dims, nullptr, s);
+    else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
+    mark(2);
+    k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, free_list, ctl, sc, job);
+    mark(3);
+    if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, ctl, dims, s);
+    else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(4);
 }
 
-void wf_iteration(const PoolView& pool, const ShadowView& sq, int* free_list, int* replay_list, Control* ctl,
-                  const SceneDev& sc, const JobParams& job, int traversal, bool count, const LaunchDims& dims,
-                  cudaStream_t s, cudaEvent_t* marks) {
+void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const JobParams& job,
+                  int traversal, bool count, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks) {
     if (traversal == TRT_TRAVERSE_REF) {
-        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
-        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
+        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, job, dims, s, marks);
+        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, job, dims, s, marks);
     } else {
-        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
-        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, sq, free_list, replay_list, ctl, sc, job, dims, s, marks);
+        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, job, dims, s, marks);
+        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, job, dims, s, marks);
     }
 }
 
 void wf_trace_primary(const SceneDev& sc, const JobParams& job, int, int traversal, int* d_id, float* d_t,
-                      float* d_ray, uint32_t* d_fetched, uint32_t* d_entered, uint32_t* d_tris, cudaStream_t s) {
+                      float* d_ray, uint32_t* d_fetched, uint32_t* d_entered, uint32_t* d_tris,
+                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
     const int n = job.rc.width * job.rc.height;
-    if (traversal == TRT_TRAVERSE_REF)
-        k_trace_primary<TRT_TRAVERSE_REF><<<grid_for(n), kBlock, 0, s>>>(sc, job, d_id, d_t, d_ray, d_fetched,
-                                                                          d_entered, d_tris);
-    else
-        k_trace_primary<TRT_TRAVERSE_FAST><<<grid_for(n), kBlock, 0, s>>>(sc, job, d_id, d_t, d_ray, d_fetched,
-                                                                           d_entered, d_tris);
+    if (traversal == TRT_TRAVERSE_REF) {
+        k_trace_primary_ref<<<grid_for(n), kBlock, 0, s>>>(sc, job, d_id, d_t, d_ray, d_fetched, d_entered, d_tris);
+        return;
+    }
+    // FAST: the production persistent kernel over a scratch pool; "entered" reports replayed rays
+    k_pack_primary<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, job, d_ray);
+    k_reset_cursors<<<1, 32, 0, s>>>(ctl);
+    extend_fast<false>(scratch, sc, ctl, dims, reinterpret_cast<int*>(d_entered), s);
+    k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_id, d_t);
+    (void)d_fetched;
+    (void)d_tris;
 }
 
 void wf_trace_closest(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_id, float* d_t,
-                      cudaStream_t s) {
-    if (traversal == TRT_TRAVERSE_REF)
-        k_trace_closest<TRT_TRAVERSE_REF><<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_id, d_t);
-    else
-        k_trace_closest<TRT_TRAVERSE_FAST><<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_id, d_t);
+                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
+    if (traversal == TRT_TRAVERSE_REF) {
+        k_trace_closest_ref<<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_id, d_t);
+        return;
+    }
+    k_pack_rays<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, d_rays, n);
+    k_reset_cursors<<<1, 32, 0, s>>>(ctl);
+    extend_fast<false>(scratch, sc, ctl, dims, nullptr, s);
+    k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_id, d_t);
 }
 
-void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ, cudaStream_t s) {
-    if (traversal == TRT_TRAVERSE_REF)
-        k_trace_shadow<TRT_TRAVERSE_REF><<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_occ);
-    else
-        k_trace_shadow<TRT_TRAVERSE_FAST><<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_occ);
+void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ,
+                     const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
+    if (traversal == TRT_TRAVERSE_REF) {
+        k_trace_shadow_ref<<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_occ);
+        return;
+    }
+    k_pack_rays<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, d_rays, n);
+    k_reset_cursors<<<1, 32, 0, s>>>(ctl);
+    shadow_fast<false>(scratch, sc, ctl, dims, s);
+    k_unpack_occluded<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_occ);
 }
 
 void wf_rng_states(const JobParams& job, int frame_local, int first_pixel, int n, uint32_t* d_states,

@@ -1,13 +1,16 @@
 // wavefront.cuh -- data layout of the streaming wavefront path tracer and the host-side
 // launch interface implemented in wavefront.cu.
 //
-// A fixed pool of P path slots lives in HBM (sized so its working set stays L2 resident).
-// Every iteration runs
+// A fixed pool of P path slots lives in HBM.  Every iteration runs
 //     prepare -> regenerate -> extend (closest hit) -> shade -> shadow (any hit)
 // over the pool.  Paths that end are accumulated into the caller's buffer and their slots
 // go to a free list; `regenerate` refills those slots with the next camera samples of the
 // job, so the extend kernel always sees a full pool until the job drains.  Shadow rays are
-// compacted into their own queue with warp-aggregated atomics (__ballot_sync/__popc).
+// written IN PLACE (one per slot, a valid flag in sh_d.w): almost every diffuse vertex
+// spawns one, so compaction would buy nothing, and the persistent traversal kernels pull
+// 32-slot chunks of either ray array with TMA bulk copies.  The next-event contribution
+// waits in `pend` until the shadow kernel has had its say (it zeroes pend for occluded
+// rays); the next shade pass folds it into the path's radiance.
 #pragma once
 #include "common.cuh"
 #include "xorwow.cuh"
@@ -16,23 +19,19 @@ namespace trt {
 
 enum { SLOT_DEAD = 0, SLOT_ACTIVE = 1, SLOT_FINISH = 2 };
 
-// Path slot, SoA: 96 bytes per slot over all arrays.
+// Path slot, SoA: 144 bytes per slot over all arrays.
 struct PoolView {
     float4* ray_o;   // origin.xyz, unused
     float4* ray_d;   // direction.xyz, flags (int bits): state | depth << 8 | prev_mode << 16
     float2* hit;     // written by extend: t, hit object id (int bits, -1 = miss)
     float4* thr;     // throughput.xyz, pixel index (int bits)
     float4* rad;     // radiance.xyz, unused
+    float4* pend;    // next-event contribution of the previous vertex (throughput applied), unused
+    float4* sh_o;    // shadow ray of this slot: origin.xyz, max_dist
+    float4* sh_d;    // direction.xyz, valid flag (int bits, 1 = trace it)
     uint4* rng_a;    // XORWOW v0..v3
     uint2* rng_b;    // XORWOW v4, d
-    int capacity;
-};
-
-// Shadow-ray queue entry, SoA: 48 bytes.
-struct ShadowView {
-    float4* o;  // origin.xyz, max_dist
-    float4* d;  // direction.xyz, slot (int bits)
-    float4* c;  // contribution.rgb (throughput already applied)
+    int capacity;    // multiple of 256
 };
 
 // Device-resident control block (one per context).
@@ -42,7 +41,7 @@ struct Control {
     int n_free;        // free-list entries appended by the last shade pass
     int n_regen;       // slots to regenerate this iteration
     unsigned long long regen_base;  // first sample index for this iteration's regeneration
-    int n_shadow;      // shadow-queue entries appended by the last shade pass
+    int n_shadow;      // unused (shadow rays are in place)
     int alive;         // slots that hold a live path
     int cursor_extend, cursor_shadow, cursor_replay;
     int n_replay;
@@ -67,9 +66,16 @@ struct JobParams {
 
 struct LaunchDims {
     int sms;
-    int fast_blocks_per_sm;  // resident CTAs per SM of the persistent traversal kernels
-    int fast_variant;        // 4, 6 or 8: __launch_bounds__ min-blocks variant (register budget)
+    int fast_threads;   // threads of the persistent traversal CTAs (one CTA per SM): 512, 768 or 1024
+    int smem_nodes;     // wide nodes staged into shared memory per CTA (top of the tree)
+    int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
+    int tri_min;        // closest hit: lanes with a pending triangle needed to run the triangle step
 };
+
+// shared-memory bytes the persistent kernels need for a given configuration (0 = unsupported)
+size_t wf_fast_smem_bytes(int threads, int smem_nodes, bool shadow);
+// largest node count that fits beside the stacks and the ray staging buffers
+int wf_fast_max_smem_nodes(int threads, size_t smem_limit);
 
 // ---- launchers (wavefront.cu) --------------------------------------------------------
 void wf_init_pool(const PoolView& pool, int* free_list, Control* ctl, cudaStream_t s);
@@ -80,16 +86,21 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
 // one wavefront iteration (five kernels) on stream s
 // `marks`, when not null, receives five events recorded at the kernel boundaries of the
 // iteration: [prepare+regenerate] m1 [extend] m2 [shade] m3 [shadow] m4  (m0 first).
-void wf_iteration(const PoolView& pool, const ShadowView& sq, int* free_list, int* replay_list, Control* ctl,
-                  const SceneDev& sc, const JobParams& job, int traversal, bool count, const LaunchDims& dims,
-                  cudaStream_t s, cudaEvent_t* marks = nullptr);
+void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const JobParams& job,
+                  int traversal, bool count, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks = nullptr);
+// one-time opt-in to large dynamic shared memory for the persistent kernels
+int wf_configure();
 int wf_kernels_per_iteration(int traversal);
 
+// Parity / test entry points.  In FAST mode they run the production persistent kernels over a
+// scratch pool (`scratch`, capacity >= n rounded up to 256; `ctl` is the context's control block).
 void wf_trace_primary(const SceneDev& sc, const JobParams& job, int frame_seed, int traversal, int* d_id, float* d_t,
-                      float* d_ray, uint32_t* d_fetched, uint32_t* d_entered, uint32_t* d_tris, cudaStream_t s);
+                      float* d_ray, uint32_t* d_fetched, uint32_t* d_entered, uint32_t* d_tris,
+                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s);
 void wf_trace_closest(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_id, float* d_t,
-                      cudaStream_t s);
-void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ, cudaStream_t s);
+                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s);
+void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ,
+                     const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s);
 void wf_rng_states(const JobParams& job, int frame_local, int first_pixel, int n, uint32_t* d_states, cudaStream_t s);
 void wf_tonemap(const float* d_accum, int n_pixels, int frames, uint32_t* d_argb, cudaStream_t s);
 
