@@ -69,6 +69,7 @@ struct trt_ctx {
     std::vector<cudaArray_t> tex_arrays;
     std::vector<cudaTextureObject_t> tex_objs;
     SceneDev sc{};
+    TopPrims top{};
     trt_scene_info info{};
 
     // XORWOW tables
@@ -102,6 +103,12 @@ struct trt_ctx {
 };
 
 namespace {
+
+float __int_as_float_host(int i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
 
 int use_device(trt_ctx* c) {
     CU(cudaSetDevice(c->device));
@@ -244,24 +251,24 @@ int ensure_scratch(trt_ctx* c, int n) {
     return 0;
 }
 
-// Launch configuration of the persistent traversal kernels.  Defaults: 512-thread CTAs, as much
-// of the top of the tree in shared memory as fits beside the stacks while leaving L1 room for
-// the triangle records.  TRT_FAST_THREADS / TRT_SMEM_NODES / TRT_REFILL override (tuning).
+// Launch configuration of the persistent traversal kernels.  Defaults from the B200 sweep
+// (profiles/): 768-thread CTAs (24 warps/SM at 80 registers), no node staging -- with the scene
+// L1-resident, staging the top of the tree into shared memory measured no faster than leaving
+// L1 to cache it, and the shared memory is better spent on stacks and ray queues.
+// TRT_FAST_THREADS / TRT_SMEM_NODES / TRT_REFILL override (tuning).
 LaunchDims launch_dims(const trt_ctx* c) {
     LaunchDims d;
     d.sms = c->sms;
-    d.fast_threads = 512;
+    d.fast_threads = 768;
     if (const char* e = getenv("TRT_FAST_THREADS")) {
         const int v = atoi(e);
         if (v == 512 || v == 768 || v == 1024) d.fast_threads = v;
     }
     const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
-    d.smem_nodes = std::min(fit, 768);
+    d.smem_nodes = 0;
     if (const char* e = getenv("TRT_SMEM_NODES")) d.smem_nodes = std::max(0, std::min(fit, atoi(e)));
     d.refill_below = 25;
     if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
-    d.tri_min = 1;
-    if (const char* e = getenv("TRT_TRI_MIN")) d.tri_min = std::max(1, std::min(32, atoi(e)));
     return d;
 }
 
@@ -333,7 +340,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
                     marks = c->marks.data() + c->marks_used;
                     c->marks_used += 5;
                 }
-                wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, job, o.traversal, o.count_rays != 0, dims,
+                wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, c->top, job, o.traversal, o.count_rays != 0, dims,
                              c->stream, marks);
             }
             c->launches += (unsigned long long)kBatchIterations * kpi;
@@ -504,6 +511,20 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
     sc.n_wide_nodes = (int)wb.nodes.size();
     sc.n_tris = (int)wb.tris.size();
 
+    TopPrims& tp = c->top;
+    memset(&tp, 0, sizeof(tp));
+    tp.n = (int)wb.top.size();
+    for (int i = 0; i < tp.n; i++) {
+        const TopPrim& t = wb.top[i];
+        tp.v0[i] = make_float4(t.v0[0], t.v0[1], t.v0[2], __int_as_float_host(t.id));
+        tp.e1[i] = make_float4(t.e1[0], t.e1[1], t.e1[2], 0.f);
+        tp.e2[i] = make_float4(t.e2[0], t.e2[1], t.e2[2], 0.f);
+        tp.bmin[i] = make_float4(t.mn[0], t.mn[1], t.mn[2], 0.f);
+        tp.bmax[i] = make_float4(t.mx[0], t.mx[1], t.mx[2], 0.f);
+    }
+    tp.root_lo = make_float4(wb.root_mn[0], wb.root_mn[1], wb.root_mn[2], 0.f);
+    tp.root_hi = make_float4(wb.root_mx[0], wb.root_mx[1], wb.root_mx[2], 0.f);
+
     trt_scene_info& in = c->info;
     memset(&in, 0, sizeof(in));
     in.n_objects = n_objects;
@@ -569,8 +590,8 @@ int trt_trace_primary(trt_ctx* c, int w, int h, int frame_seed, const void* cam,
     fill_job(c, job, nullptr, w, h, frame_seed, 1, 1, cam, o);
     if (int rc = ensure_scratch(c, w * h)) return rc;
     wf_col_table(c->d_col_pows, c->n_col_bits, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
-    wf_trace_primary(c->sc, job, frame_seed, traversal, d_id, d_t, d_ray, d_fetched, d_entered, d_tris, c->scratch,
-                     c->d_ctl, launch_dims(c), c->stream);
+    wf_trace_primary(c->sc, job, frame_seed, traversal, d_id, d_t, d_ray, d_fetched, d_entered, d_tris, c->top,
+                     c->scratch, c->d_ctl, launch_dims(c), c->stream);
     c->launches += 2;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -583,7 +604,7 @@ int trt_trace_closest(trt_ctx* c, const float* d_rays, int n, int traversal, int
     if (n <= 0) return 0;
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_scratch(c, n)) return rc;
-    wf_trace_closest(c->sc, d_rays, n, traversal, d_id, d_t, c->scratch, c->d_ctl, launch_dims(c), c->stream);
+    wf_trace_closest(c->sc, d_rays, n, traversal, d_id, d_t, c->top, c->scratch, c->d_ctl, launch_dims(c), c->stream);
     c->launches += 1;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -596,7 +617,7 @@ int trt_trace_shadow(trt_ctx* c, const float* d_rays, int n, int traversal, int*
     if (n <= 0) return 0;
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_scratch(c, n)) return rc;
-    wf_trace_shadow(c->sc, d_rays, n, traversal, d_occ, c->scratch, c->d_ctl, launch_dims(c), c->stream);
+    wf_trace_shadow(c->sc, d_rays, n, traversal, d_occ, c->top, c->scratch, c->d_ctl, launch_dims(c), c->stream);
     c->launches += 1;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());

@@ -199,6 +199,8 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
         LeafBox& lb = out.leaf_boxes[o];
         for (int k = 0; k < 3; k++) { lb.mn[k] = pbox[o].mn[k]; lb.mx[k] = pbox[o].mx[k]; }
     }
+    out.top.clear();
+    for (int k = 0; k < 3; k++) { out.root_mn[k] = INFINITY; out.root_mx[k] = -INFINITY; }
     if (live.empty()) {
         WideNode n;
         clear_node(n);
@@ -215,7 +217,7 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
             const float aa = pbox[a].area(), ab = pbox[b].area();
             return aa != ab ? aa > ab : a < b;
         });
-        const size_t max_top = 12;
+        const size_t max_top = kMaxTopPrims;
         std::vector<char> is_top(n_objects, 0);
         if (live.size() > 16)
             for (size_t i = 0; i < by_area.size() && top.size() < max_top; i++) {
@@ -234,66 +236,21 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
     bld.order = rest;
     const int mesh_root = bld.build(0, (int)rest.size());
 
-    // 4. small exact-SAH binary tree over {mesh subtree, top primitives}
-    struct Item { Box box; int bnode; int prim; };
-    std::vector<Item> items;
-    items.push_back(Item{bld.nodes[mesh_root].box, mesh_root, -1});
-    for (int o : top) items.push_back(Item{pbox[o], -1, o});
-    // extra leaves for top prims are appended to the builder's node list
-    std::vector<int> top_order;  // objects referenced by top leaves, appended after `rest`
-    const int rest_count = (int)rest.size();
-    std::function<int(std::vector<int>)> build_top = [&](std::vector<int> idx) -> int {
-        if (idx.size() == 1) {
-            const Item& it = items[idx[0]];
-            if (it.bnode >= 0) return it.bnode;
-            const int self = (int)bld.nodes.size();
-            bld.nodes.emplace_back();
-            bld.nodes[self].box = it.box;
-            bld.nodes[self].first = rest_count + (int)top_order.size();
-            bld.nodes[self].count = 1;
-            top_order.push_back(it.prim);
-            return self;
-        }
-        // best (axis, split) by full sweep on box centres
-        float best = INFINITY;
-        int best_axis = 0;
-        size_t best_k = idx.size() / 2;
-        for (int axis = 0; axis < 3; axis++) {
-            std::vector<int> s = idx;
-            std::sort(s.begin(), s.end(), [&](int a, int b) {
-                return items[a].box.mn[axis] + items[a].box.mx[axis] < items[b].box.mn[axis] + items[b].box.mx[axis];
-            });
-            for (size_t k = 1; k < s.size(); k++) {
-                Box l, r;
-                l.reset(); r.reset();
-                for (size_t i = 0; i < k; i++) l.grow(items[s[i]].box);
-                for (size_t i = k; i < s.size(); i++) r.grow(items[s[i]].box);
-                const float c = l.area() * k + r.area() * (s.size() - k);
-                if (c < best) { best = c; best_axis = axis; best_k = k; }
-            }
-        }
-        std::vector<int> s = idx;
-        const int axis = best_axis;
-        std::sort(s.begin(), s.end(), [&](int a, int b) {
-            return items[a].box.mn[axis] + items[a].box.mx[axis] < items[b].box.mn[axis] + items[b].box.mx[axis];
-        });
-        std::vector<int> lv(s.begin(), s.begin() + best_k), rv(s.begin() + best_k, s.end());
-        const int l = build_top(lv);
-        const int r = build_top(rv);
-        const int self = (int)bld.nodes.size();
-        bld.nodes.emplace_back();
-        Box b = bld.nodes[l].box;
-        b.grow(bld.nodes[r].box);
-        bld.nodes[self].box = b;
-        bld.nodes[self].left = l;
-        bld.nodes[self].right = r;
-        return self;
-    };
-    std::vector<int> all(items.size());
-    std::iota(all.begin(), all.end(), 0);
-    const int root = build_top(all);
-    std::vector<int> order = bld.order;
-    order.insert(order.end(), top_order.begin(), top_order.end());
+    // 4. the root-level list
+    const int root = mesh_root;
+    const std::vector<int>& order = bld.order;
+    out.top.clear();
+    for (int o : top) {
+        const Object& ob = objects[o];
+        TopPrim tp;
+        tp.v0[0] = ob.v0.x; tp.v0[1] = ob.v0.y; tp.v0[2] = ob.v0.z;
+        tp.id = o;
+        tp.e1[0] = add_ftz(ob.v1.x, -ob.v0.x); tp.e1[1] = add_ftz(ob.v1.y, -ob.v0.y); tp.e1[2] = add_ftz(ob.v1.z, -ob.v0.z);
+        tp.e2[0] = add_ftz(ob.v2.x, -ob.v0.x); tp.e2[1] = add_ftz(ob.v2.y, -ob.v0.y); tp.e2[2] = add_ftz(ob.v2.z, -ob.v0.z);
+        for (int k = 0; k < 3; k++) { tp.mn[k] = pbox[o].mn[k]; tp.mx[k] = pbox[o].mx[k]; }
+        out.top.push_back(tp);
+    }
+    for (int k = 0; k < 3; k++) { out.root_mn[k] = bld.nodes[root].box.mn[k]; out.root_mx[k] = bld.nodes[root].box.mx[k]; }
 
     // 5. triangle records in leaf order
     out.tris.resize(order.size());

@@ -7,7 +7,9 @@
 //     contains the reference leaf boxes below it, which is what makes the fast traversal a
 //     strict superset of the reference traversal (kernels/traverse_wide.cuh);
 //   * oversized primitives (the room's one-triangle walls) lifted out of
-//     the SAH tree and attached near the root, where they stop inflating every upper box;
+//     the SAH tree into a short root-level list (`top`, at most kMaxTopPrims): the traversal
+//     kernels test that list brute force, fully converged, before a ray ever enters the tree,
+//     so the giant boxes neither inflate the upper levels nor cost stack traffic;
 //   * 48-byte triangle records (v0, v1, v2 as three float4) in wide-leaf order; the kernels
 //     subtract the edges per test exactly as the reference does, and re-derive the reference
 //     leaf box (bounds of the three vertices + the builder's padding rule) to decide exactly
@@ -48,8 +50,22 @@ struct LeafBox {  // 32 bytes
     float mn[4], mx[4];
 };
 
+constexpr int kMaxTopPrims = 12;
+
+// A root-level primitive: vertices as (v0, e1 = v1 - v0, e2 = v2 - v0) with the single FTZ
+// rounding the reference applies per test (reference src/renderer.cu:239-240), and its
+// reference leaf box as uploaded.
+struct TopPrim {
+    float v0[3];
+    int id;
+    float e1[3], e2[3];
+    float mn[3], mx[3];
+};
+
 struct WideBvh {
-    std::vector<WideNode> nodes;  // root = 0
+    std::vector<WideNode> nodes;  // root = 0; the tree covers every object that is not in `top`
+    std::vector<TopPrim> top;     // root-level list (oversized primitives)
+    float root_mn[3] = {0, 0, 0}, root_mx[3] = {0, 0, 0};  // bounds of the tree (inverted when empty)
     std::vector<TriRecord> tris;
     std::vector<LeafBox> leaf_boxes;  // per object id
     int n_top_prims = 0;

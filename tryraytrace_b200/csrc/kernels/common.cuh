@@ -77,6 +77,21 @@ struct SceneDev {
     int n_wide_nodes, n_tris;
 };
 
+// Root-level primitive list (host/wide_bvh.h TopPrim), handed to the traversal kernels BY VALUE:
+// it lives in the constant bank, every lane reads the same record, and the brute-force pass over
+// it runs fully converged before a ray enters the tree.  root_lo/root_hi bound the tree.
+constexpr int kMaxTop = 12;
+struct TopPrims {
+    float4 v0[kMaxTop];    // v0.xyz, object id (int bits)
+    float4 e1[kMaxTop];    // v1 - v0 (single FTZ rounding, as reference :239), unused
+    float4 e2[kMaxTop];    // v2 - v0
+    float4 bmin[kMaxTop];  // reference leaf box as uploaded
+    float4 bmax[kMaxTop];
+    float4 root_lo, root_hi;
+    int n;
+    int _pad[3];
+};
+
 struct RenderConsts {
     int width, height;
     int max_depth, rr_threshold;

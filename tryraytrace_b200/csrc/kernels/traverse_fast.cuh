@@ -24,8 +24,16 @@
 //     to the lowest object index, as the reference's ascending leaf order does.
 // Any-hit queries have a fixed interval, so (3) decides them exactly and no replay exists.
 //
-// Execution model (kernels in wavefront.cu).  One persistent CTA per SM.  A warp holds 32 rays;
-// the traversal is written as ROUNDS so the lanes stay converged: in every round a lane performs
+// Execution model (kernels in wavefront.cu).  One persistent CTA per SM.  Two levels:
+//   * TOP PHASE.  A warp takes a chunk of 32 consecutive pool slots, one ray per lane, and tests
+//     the root-level list (the oversized primitives the builder lifted out of the tree, <= 12,
+//     in the constant bank) brute force and fully converged, plus the tree's bounding box.  In
+//     the benchmark scenes ~3/4 of all rays are decided right there (they only ever see the
+//     room's walls) at 100% lane utilisation and without touching a stack.
+//   * TREE PHASE.  Rays that enter the tree are compacted (__ballot_sync/__popc) into a per-warp
+//     queue in shared memory, carrying the d_min / id found so far; idle traversal lanes refill
+//     from that queue.
+// The tree traversal is written as ROUNDS so the lanes stay converged: in every round a lane performs
 // at most one wide-node step (four child-box tests) and at most one triangle step.  Inner
 // children go to a per-lane node stack, leaf children to a separate per-lane triangle stack;
 // both live in SHARED memory (lane-interleaved, conflict free), with a local-memory overflow
@@ -218,42 +226,71 @@ struct ClosestRay {
     bool amb;
 };
 
-TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, uint32_t base, uint32_t ttop) {
+// Tree-phase entry: the ray with the d_min / id / ambiguity the top phase found.
+TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, float d_min, int id, bool amb,
+                           uint32_t base, uint32_t ttop) {
     s.o = f3(o4.x, o4.y, o4.z);
     s.d = f3(d4.x, d4.y, d4.z);
     s.inv = f3(ref_safe_inv(s.d.x), ref_safe_inv(s.d.y), ref_safe_inv(s.d.z));
     s.nxo = s.inv.x < 0.f ? 16 : 0;
     s.nyo = s.inv.y < 0.f ? 48 : 32;
     s.nzo = s.inv.z < 0.f ? 80 : 64;
-    s.d_min = 1e20f;
-    s.id = -1;
-    s.amb = false;
+    s.d_min = d_min;
+    s.id = id;
+    s.amb = amb;
     s.np = base;
     s.tp = ttop;
     s.nspill = 0;
     s.cur = 0;  // root
 }
 
+// TOP PHASE, closest hit: the root-level list, brute force, same accept rule as the tree phase
+// (exact triangle arithmetic, exact leaf-box reach, lowest id on ties, ambiguity flag), then the
+// tree's bounding box against [0, d_min].  Every lane of the warp runs this for its own ray.
+struct TopResult {
+    float d_min;
+    int id;
+    bool amb;
+    bool enters;  // the ray can reach something in the tree
+};
+TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
+    const F3 inv = f3(ref_safe_inv(d.x), ref_safe_inv(d.y), ref_safe_inv(d.z));
+    const bool sx = inv.x < 0.f, sy = inv.y < 0.f, sz = inv.z < 0.f;
+    TopResult r;
+    r.d_min = 1e20f;
+    r.id = -1;
+    r.amb = false;
+#pragma unroll 1
+    for (int p = 0; p < top.n; p++) {
+        const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
+        const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
+        const int tid = f2i(a.w);
+        float entry;
+        const bool reach = leaf_box_reach(top.bmin[p], top.bmax[p], o, inv, sx, sy, sz, &entry);
+        if (reach && t > 0.f && (t < r.d_min || (t == r.d_min && tid < r.id))) {
+            if (entry < t) { r.d_min = t; r.id = tid; }
+            else r.amb = true;
+        }
+    }
+    float tn;
+    const float limit = r.d_min * kCullSlack;
+    r.enters = child_interval(sx ? top.root_hi.x : top.root_lo.x, sx ? top.root_lo.x : top.root_hi.x,
+                              sy ? top.root_hi.y : top.root_lo.y, sy ? top.root_lo.y : top.root_hi.y,
+                              sz ? top.root_hi.z : top.root_lo.z, sz ? top.root_lo.z : top.root_hi.z, o, inv, 0.f,
+                              limit, &tn);
+    return r;
+}
+
 // One round for one lane; called by ALL lanes of the warp (a lane without a ray has empty stacks
 // and nothing happens for it).  E = bytes between consecutive entries of this lane, S = entries.
-// `tri_min`: the triangle step runs only when at least that many lanes have a triangle waiting,
-// or when some lane cannot make progress without it -- triangle tests are then executed by
-// fuller warps (speculative while-while, Aila & Laine 2009).
 template <uint32_t E, int S, bool COUNT>
 TRT_DEV bool closest_round(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ClosestRay& s, uint32_t base,
-                           uint2* spill, WideCounts* wc, int tri_min) {
+                           uint2* spill, WideCounts* wc) {
     const uint32_t ttop = base + (S - 1) * E;
     const float limit = s.d_min * kCullSlack;
     // at least four free entries (a node step can push that many); tp - np = (free - 1) * E, signed:
     // a completely full stack gives -E
     const bool room = (int)(s.tp - s.np) >= (int)(3 * E);
-    {
-        const bool has_tri = s.tp != ttop;
-        const bool node_work = s.cur != kWideEmptyRef || s.np != base || s.nspill > 0;
-        const unsigned m_tri = __ballot_sync(0xffffffffu, has_tri);
-        const unsigned m_urgent = __ballot_sync(0xffffffffu, has_tri && (!room || !node_work));
-        if (__popc(m_tri) < tri_min && m_urgent == 0) tri_min = -1;  // skip the triangle step this round
-    }
     // ---- choose this round's node: the held one, else the nearest-first stack --------------
     int node = kWideEmptyRef;
     if (room) {
@@ -280,7 +317,7 @@ TRT_DEV bool closest_round(const unsigned char* s_nodes, int k_smem, const Scene
     }
     // ---- choose this round's triangle -------------------------------------------------------
     int tri = -1;
-    while (tri_min >= 0 && s.tp != ttop) {
+    while (s.tp != ttop) {
         const uint32_t top = s.tp + E;
         const uint2 e = lds64(top);
         if (!(__uint_as_float(e.x) < limit)) { s.tp = top; continue; }
@@ -376,6 +413,29 @@ TRT_DEV void shadow_begin(ShadowRay& s, const float4 o4, const float4 d4, uint32
     s.np = base + E;
     s.tp = ttop;
     s.nspill = 0;
+}
+
+// TOP PHASE, any hit: returns 1 = occluded by a root-level primitive, 2 = must traverse the tree,
+// 0 = unoccluded.  Same exact tests as the tree phase.
+TRT_DEV int top_shadow(const TopPrims& top, const F3 o, const F3 d, float max_dist) {
+    const F3 inv = f3(p_rcp(d.x), p_rcp(d.y), p_rcp(d.z));  // raw reciprocal, reference :276
+    const float t_hi = p_sub(max_dist, 0.001f);
+    bool occluded = false;
+#pragma unroll 1
+    for (int p = 0; p < top.n; p++) {
+        const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
+        const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
+        const bool reach = ref_slab(top.bmin[p], top.bmax[p], o, inv, 0.001f, max_dist);
+        occluded = occluded || (t > 0.001f && t < t_hi && reach);
+    }
+    if (occluded) return 1;
+    float tn;
+    const bool sx = inv.x < 0.f, sy = inv.y < 0.f, sz = inv.z < 0.f;
+    const bool enters = child_interval(sx ? top.root_hi.x : top.root_lo.x, sx ? top.root_lo.x : top.root_hi.x,
+                                       sy ? top.root_hi.y : top.root_lo.y, sy ? top.root_lo.y : top.root_hi.y,
+                                       sz ? top.root_hi.z : top.root_lo.z, sz ? top.root_lo.z : top.root_hi.z, o, inv,
+                                       0.001f, max_dist, &tn);
+    return enters ? 2 : 0;
 }
 
 template <uint32_t E, int S, bool COUNT>

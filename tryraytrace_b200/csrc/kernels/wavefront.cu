@@ -291,18 +291,26 @@ __global__ void __launch_bounds__(kBlock) k_shadow_ref(PoolView pool, SceneDev s
     }
 }
 
-// ---- persistent fast-path kernels: while-while traversal with dynamic ray fetch -------------
+// ---- persistent fast-path kernels: two-level while-while traversal with dynamic ray fetch ------
 // One CTA per SM.  Shared memory, in order:
 //   [ top-of-tree nodes: k_smem x 128 B ][ per-thread stacks: S x THREADS entries ]
 //   [ per-warp ray staging: 2 buffers x (32 origins + 32 directions) x 16 B ][ per-warp mbarriers ]
-// A warp holds 32 rays.  Rounds (traverse_fast.cuh) keep the lanes converged; a lane whose ray has
-// finished writes its result and goes idle; when fewer than `refill_below` lanes hold a ray the
-// idle lanes take the next rays from the warp's staging buffer.  The buffer is refilled a chunk
-// (32 consecutive slots) at a time: lane 0 claims the chunk with one atomicAdd on a global
-// cursor and issues two TMA bulk copies (origins, directions) that complete on an mbarrier; the
-// copy for chunk r+1 is in flight while chunk r is being traced.
+//   [ per-warp tree-ray queue: kQueueCap entries ]
+// A warp repeatedly
+//   1. takes a chunk of 32 consecutive pool slots -- lane 0 claims it with one atomicAdd on a global
+//      cursor and issues two TMA bulk copies (origins, directions) that complete on an mbarrier;
+//      the copy for chunk r+1 is in flight while chunk r is processed -- and runs the TOP PHASE on
+//      it, one ray per lane, fully converged (traverse_fast.cuh).  Rays decided there write their
+//      result at once; rays that enter the tree are compacted into the warp's queue;
+//   2. refills idle traversal lanes from the queue when fewer than `refill_below` lanes hold a ray;
+//   3. runs one traversal ROUND for the rays it holds (at most one node step and one triangle
+//      step per lane).
 constexpr int kChunk = 32;
 constexpr int kStageBytesPerWarp = 2 * 2 * kChunk * 16;  // 2 buffers x (o + d) x 32 x float4
+constexpr int kQueueCap = 64;                             // entries; the top phase runs while <= kQueueLow are queued
+constexpr int kQueueLow = kQueueCap - kChunk;
+constexpr int kQueueBytesClosest = kQueueCap * (16 + 16 + 4);
+constexpr int kQueueBytesShadow = kQueueCap * (16 + 16);
 
 template <int THREADS> struct FastCfg;
 template <> struct FastCfg<512>  { static constexpr int SC = 16, SS = 16; };
@@ -310,28 +318,29 @@ template <> struct FastCfg<768>  { static constexpr int SC = 12, SS = 12; };
 template <> struct FastCfg<1024> { static constexpr int SC = 8,  SS = 10; };
 
 struct Feeder {  // warp-uniform state of the staging double buffer
-    int cur_buf, cur_pos, cur_base, nxt_base;
-    bool nxt_req, drained;
+    int cur_buf, cur_base, nxt_base;
+    bool fresh;    // the current buffer holds a chunk that has not been processed yet
+    bool nxt_req;  // a bulk copy into the other buffer has been issued
+    bool drained;  // the global cursor ran past the pool
     unsigned phase;  // bit b = parity the next wait on buffer b uses
 };
 
 TRT_DEV void feeder_init(Feeder& f) {
     f.cur_buf = 0;
-    f.cur_pos = kChunk;
     f.cur_base = 0;
     f.nxt_base = 0;
+    f.fresh = false;
     f.nxt_req = false;
     f.drained = false;
     f.phase = 0;
 }
-TRT_DEV bool feeder_exhausted(const Feeder& f) { return f.drained && f.cur_pos >= kChunk && !f.nxt_req; }
+TRT_DEV bool feeder_exhausted(const Feeder& f) { return f.drained && !f.fresh && !f.nxt_req; }
 
-// Advance the double buffer: swap in the prefetched chunk when the current one is used up, and
-// request the chunk after it.  `block` = nobody in the warp has work, so waiting is all there is
-// to do.  Returns with f.cur_pos < kChunk when rays can be handed out.
+// Make the next chunk current if it has landed (or wait for it when `block`: nobody in the warp
+// has anything else to do), and keep one chunk in flight behind it.
 TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const float4* src_o, const float4* src_d,
                             int* cursor, int limit, unsigned lane, bool block) {
-    if (f.cur_pos >= kChunk && f.nxt_req) {
+    if (!f.fresh && f.nxt_req) {
         const int nb = f.cur_buf ^ 1;
         const uint32_t parity = (f.phase >> nb) & 1u;
         int ready = 0;
@@ -345,8 +354,8 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
         if (ready) {
             f.phase ^= 1u << nb;
             f.cur_buf = nb;
-            f.cur_pos = 0;
             f.cur_base = f.nxt_base;
+            f.fresh = true;
             f.nxt_req = false;
         }
     }
@@ -372,14 +381,16 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
 
 template <int THREADS, bool COUNT>
 __global__ void __launch_bounds__(THREADS, 1)
-k_extend_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_below, int tri_min, int* amb_out) {
+k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
+              int refill_below, int* amb_out) {
     constexpr int S = FastCfg<THREADS>::SC;
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_nodes = smem;
     uint2* s_stack = reinterpret_cast<uint2*>(smem + (size_t)k_smem * 128);
     float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
-    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) +
-                                                   (THREADS / 32) * kStageBytesPerWarp);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
+    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
@@ -393,6 +404,9 @@ k_extend_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_b
 
     float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
     uint64_t* bars = s_bars + warp * 2;
+    float4* q_o = reinterpret_cast<float4*>(s_queue + warp * kQueueBytesClosest);  // origin, d_min
+    float4* q_d = q_o + kQueueCap;                                                  // direction, (id + 1) | amb << 31
+    int* q_s = reinterpret_cast<int*>(q_d + kQueueCap);                             // pool slot
     constexpr uint32_t E = THREADS * 8;  // bytes between consecutive stack entries of one lane
     const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
     const uint32_t stk_ttop = stk_base + (S - 1) * E;
@@ -407,34 +421,67 @@ k_extend_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_b
     WideCounts wc = {0, 0};
     bool has = false;
     int slot = -1;
+    int qn = 0;  // warp-uniform: entries in the tree-ray queue
     unsigned replays = 0, rays = 0;
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
-        if (__popc(act) < refill_below && !feeder_exhausted(fd)) {
-            feeder_advance(fd, stage, bars, pool.ray_o, pool.ray_d, &ctl->cursor_extend, pool.capacity, lane, act == 0);
-            if (fd.cur_pos < kChunk) {
-                const unsigned idle = ~act;
-                const int my = fd.cur_pos + __popc(idle & lt_mask);
-                if (!has && my < kChunk) {
-                    const float4* buf = stage + fd.cur_buf * (2 * kChunk);
-                    const float4 d4 = buf[kChunk + my];
-                    if ((f2i(d4.w) & 0xff) == SLOT_ACTIVE) {
-                        closest_begin(st, buf[my], d4, stk_base, stk_ttop);
-                        has = true;
-                        slot = fd.cur_base + my;
-                        rays++;
-                    }
+        // 1. top phase on fresh chunks while the queue has room for a whole chunk
+        while (qn <= kQueueLow && !feeder_exhausted(fd)) {
+            feeder_advance(fd, stage, bars, pool.ray_o, pool.ray_d, &ctl->cursor_extend, pool.capacity, lane,
+                           act == 0 && qn == 0);
+            if (!fd.fresh) break;  // the next chunk has not landed: traverse meanwhile
+            const float4* buf = stage + fd.cur_buf * (2 * kChunk);
+            const float4 o4 = buf[lane], d4 = buf[kChunk + lane];
+            const bool live = (f2i(d4.w) & 0xff) == SLOT_ACTIVE;
+            const int my_slot = fd.cur_base + (int)lane;
+            TopResult tr = top_closest(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+            if (live) rays++;
+            if (live && !tr.enters) {  // decided by the root-level list alone
+                if (tr.amb) {  // rare: order-dependent reach, re-run in reference order
+                    Ray r;
+                    r.o = f3(o4.x, o4.y, o4.z);
+                    r.d = f3(d4.x, d4.y, d4.z);
+                    VisitCounts vc = {0, 0, 0};
+                    tr.id = ref_closest<false>(sc, r, &tr.d_min, &vc);
+                    replays++;
                 }
-                fd.cur_pos = min(kChunk, fd.cur_pos + __popc(idle));
-                act = __ballot_sync(0xffffffffu, has);
+                st_cs_f2(&pool.hit[my_slot], make_float2(tr.d_min, i2f(tr.id)));
+                if (amb_out) amb_out[my_slot] = tr.amb ? 1 : 0;
             }
+            const bool tree = live && tr.enters;
+            const unsigned m = __ballot_sync(0xffffffffu, tree);
+            if (tree) {
+                const int qi = qn + __popc(m & lt_mask);
+                q_o[qi] = make_float4(o4.x, o4.y, o4.z, tr.d_min);
+                q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f((tr.id + 1) | (tr.amb ? (int)0x80000000 : 0)));
+                q_s[qi] = my_slot;
+            }
+            qn += __popc(m);
+            fd.fresh = false;
+            __syncwarp();
+        }
+        // 2. refill idle lanes from the queue
+        if (qn > 0 && __popc(act) < refill_below) {
+            const unsigned idle = ~act;
+            const int rank = __popc(idle & lt_mask);
+            if (!has && rank < qn) {
+                const int qi = qn - 1 - rank;
+                const float4 o4 = q_o[qi], d4 = q_d[qi];
+                const int code = f2i(d4.w);
+                closest_begin(st, o4, d4, o4.w, (code & 0x7fffffff) - 1, code < 0, stk_base, stk_ttop);
+                slot = q_s[qi];
+                has = true;
+            }
+            qn = max(0, qn - __popc(idle));
+            act = __ballot_sync(0xffffffffu, has);
+            __syncwarp();
         }
         if (act == 0) {
-            if (feeder_exhausted(fd)) break;
+            if (qn == 0 && feeder_exhausted(fd)) break;
             continue;
         }
-        // every lane takes part in the round (warp votes inside); a lane without a ray has empty stacks
-        if (closest_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc, tri_min) && has) {
+        // 3. one traversal round; every lane takes part (a lane without a ray has empty stacks)
+        if (closest_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc) && has) {
             float t = st.d_min;
             int id = st.id;
             if (st.amb) {  // rare: order-dependent reach, re-run in reference order
@@ -462,14 +509,16 @@ k_extend_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_b
 
 template <int THREADS, bool COUNT>
 __global__ void __launch_bounds__(THREADS, 1)
-k_shadow_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_below) {
+k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
+              int refill_below) {
     constexpr int S = FastCfg<THREADS>::SS;
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_nodes = smem;
     uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem + (size_t)k_smem * 128);
     float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
-    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) +
-                                                   (THREADS / 32) * kStageBytesPerWarp);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
+    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
@@ -483,6 +532,8 @@ k_shadow_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_b
 
     float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
     uint64_t* bars = s_bars + warp * 2;
+    float4* q_o = reinterpret_cast<float4*>(s_queue + warp * kQueueBytesShadow);  // origin, max_dist
+    float4* q_d = q_o + kQueueCap;                                                 // direction, pool slot
     constexpr uint32_t E = THREADS * 4;
     const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
     const uint32_t stk_ttop = stk_base + (S - 1) * E;
@@ -497,38 +548,54 @@ k_shadow_fast(PoolView pool, SceneDev sc, Control* ctl, int k_smem, int refill_b
     WideCounts wc = {0, 0};
     bool has = false;
     int slot = -1;
+    int qn = 0;
     unsigned rays = 0;
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
-        if (__popc(act) < refill_below && !feeder_exhausted(fd)) {
-            feeder_advance(fd, stage, bars, pool.sh_o, pool.sh_d, &ctl->cursor_shadow, pool.capacity, lane, act == 0);
-            if (fd.cur_pos < kChunk) {
-                const unsigned idle = ~act;
-                const int my = fd.cur_pos + __popc(idle & lt_mask);
-                if (!has && my < kChunk) {
-                    const float4* buf = stage + fd.cur_buf * (2 * kChunk);
-                    const float4 d4 = buf[kChunk + my];
-                    if (f2i(d4.w) == 1) {
-                        shadow_begin(st, buf[my], d4, stk_base, stk_ttop, E);
-                        has = true;
-                        slot = fd.cur_base + my;
-                        rays++;
-                    }
-                }
-                fd.cur_pos = min(kChunk, fd.cur_pos + __popc(idle));
-                act = __ballot_sync(0xffffffffu, has);
+        while (qn <= kQueueLow && !feeder_exhausted(fd)) {
+            feeder_advance(fd, stage, bars, pool.sh_o, pool.sh_d, &ctl->cursor_shadow, pool.capacity, lane,
+                           act == 0 && qn == 0);
+            if (!fd.fresh) break;
+            const float4* buf = stage + fd.cur_buf * (2 * kChunk);
+            const float4 o4 = buf[lane], d4 = buf[kChunk + lane];
+            const bool live = f2i(d4.w) == 1;
+            const int my_slot = fd.cur_base + (int)lane;
+            const int verdict = top_shadow(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), o4.w);
+            if (live) rays++;
+            // the next-event contribution waits in pend; an occluded ray cancels it
+            if (live && verdict == 1) __stcs(&pool.pend[my_slot], make_float4(0.f, 0.f, 0.f, 0.f));
+            const bool tree = live && verdict == 2;
+            const unsigned m = __ballot_sync(0xffffffffu, tree);
+            if (tree) {
+                const int qi = qn + __popc(m & lt_mask);
+                q_o[qi] = o4;
+                q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f(my_slot));
             }
+            qn += __popc(m);
+            fd.fresh = false;
+            __syncwarp();
+        }
+        if (qn > 0 && __popc(act) < refill_below) {
+            const unsigned idle = ~act;
+            const int rank = __popc(idle & lt_mask);
+            if (!has && rank < qn) {
+                const int qi = qn - 1 - rank;
+                const float4 o4 = q_o[qi], d4 = q_d[qi];
+                shadow_begin(st, o4, d4, stk_base, stk_ttop, E);
+                slot = f2i(d4.w);
+                has = true;
+            }
+            qn = max(0, qn - __popc(idle));
+            act = __ballot_sync(0xffffffffu, has);
+            __syncwarp();
         }
         if (act == 0) {
-            if (feeder_exhausted(fd)) break;
+            if (qn == 0 && feeder_exhausted(fd)) break;
             continue;
         }
-        if (has) {
-            if (shadow_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc)) {
-                // the next-event contribution waits in pend; an occluded ray cancels it
-                if (st.occluded) __stcs(&pool.pend[slot], make_float4(0.f, 0.f, 0.f, 0.f));
-                has = false;
-            }
+        if (shadow_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc) && has) {
+            if (st.occluded) __stcs(&pool.pend[slot], make_float4(0.f, 0.f, 0.f, 0.f));
+            has = false;
         }
     }
     warp_add(&ctl->cnt_shadow, rays);
@@ -670,39 +737,41 @@ int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
 template <int THREADS>
 size_t fast_smem_bytes(int k_smem, bool shadow) {
     const size_t stack = shadow ? (size_t)FastCfg<THREADS>::SS * THREADS * 4 : (size_t)FastCfg<THREADS>::SC * THREADS * 8;
-    return (size_t)k_smem * 128 + stack + (size_t)(THREADS / 32) * (kStageBytesPerWarp + 16);
+    return (size_t)k_smem * 128 + stack +
+           (size_t)(THREADS / 32) * (kStageBytesPerWarp + 16 + (shadow ? kQueueBytesShadow : kQueueBytesClosest));
 }
 
 template <int THREADS, bool COUNT>
-void launch_extend_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims, int* amb_out,
-                        cudaStream_t s) {
+void launch_extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
+                        const LaunchDims& dims, int* amb_out, cudaStream_t s) {
     const int k = min(dims.smem_nodes, sc.n_wide_nodes);
     k_extend_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, false), s>>>(
-        pool, sc, ctl, k, dims.refill_below, dims.tri_min, amb_out);
+        pool, sc, top, ctl, k, dims.refill_below, amb_out);
 }
 template <int THREADS, bool COUNT>
-void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims,
-                        cudaStream_t s) {
+void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
+                        const LaunchDims& dims, cudaStream_t s) {
     const int k = min(dims.smem_nodes, sc.n_wide_nodes);
-    k_shadow_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, true), s>>>(pool, sc, ctl, k,
+    k_shadow_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, true), s>>>(pool, sc, top, ctl, k,
                                                                                               dims.refill_below);
 }
 
 template <bool COUNT>
-void extend_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims, int* amb_out,
-                 cudaStream_t s) {
+void extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl, const LaunchDims& dims,
+                 int* amb_out, cudaStream_t s) {
     switch (dims.fast_threads) {
-    case 1024: launch_extend_fast<1024, COUNT>(pool, sc, ctl, dims, amb_out, s); break;
-    case 768: launch_extend_fast<768, COUNT>(pool, sc, ctl, dims, amb_out, s); break;
-    default: launch_extend_fast<512, COUNT>(pool, sc, ctl, dims, amb_out, s); break;
+    case 1024: launch_extend_fast<1024, COUNT>(pool, sc, top, ctl, dims, amb_out, s); break;
+    case 768: launch_extend_fast<768, COUNT>(pool, sc, top, ctl, dims, amb_out, s); break;
+    default: launch_extend_fast<512, COUNT>(pool, sc, top, ctl, dims, amb_out, s); break;
     }
 }
 template <bool COUNT>
-void shadow_fast(const PoolView& pool, const SceneDev& sc, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
+void shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl, const LaunchDims& dims,
+                 cudaStream_t s) {
     switch (dims.fast_threads) {
-    case 1024: launch_shadow_fast<1024, COUNT>(pool, sc, ctl, dims, s); break;
-    case 768: launch_shadow_fast<768, COUNT>(pool, sc, ctl, dims, s); break;
-    default: launch_shadow_fast<512, COUNT>(pool, sc, ctl, dims, s); break;
+    case 1024: launch_shadow_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
+    case 768: launch_shadow_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
+    default: launch_shadow_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
 }
 
@@ -767,8 +836,8 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
 int wf_kernels_per_iteration(int) { return 5; }
 
 template <int MODE, bool COUNT>
-static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const JobParams& job,
-                           const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks) {
+static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+                           const JobParams& job, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
     auto mark = [&](int i) { if (marks) cudaEventRecord(marks[i], s); };
@@ -776,30 +845,32 @@ static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, c
     k_prepare<<<1, 32, 0, s>>>(ctl);
     k_regen<<<persistent < full ? persistent : full, kBlock, 0, s>>>(pool, free_list, ctl, job);
     mark(1);
-    if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, ctl, dims, nullptr, s);
+    if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, nullptr, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(2);
     k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, free_list, ctl, sc, job);
     mark(3);
-    if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, ctl, dims, s);
+    if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(4);
 }
 
-void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const JobParams& job,
-                  int traversal, bool count, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks) {
+void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, cudaStream_t s,
+                  cudaEvent_t* marks) {
     if (traversal == TRT_TRAVERSE_REF) {
-        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, job, dims, s, marks);
-        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, job, dims, s, marks);
+        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, s, marks);
+        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, s, marks);
     } else {
-        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, job, dims, s, marks);
-        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, job, dims, s, marks);
+        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, s, marks);
+        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, s, marks);
     }
 }
 
 void wf_trace_primary(const SceneDev& sc, const JobParams& job, int, int traversal, int* d_id, float* d_t,
                       float* d_ray, uint32_t* d_fetched, uint32_t* d_entered, uint32_t* d_tris,
-                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
+                      const TopPrims& top, const PoolView& scratch, Control* ctl, const LaunchDims& dims,
+                      cudaStream_t s) {
     const int n = job.rc.width * job.rc.height;
     if (traversal == TRT_TRAVERSE_REF) {
         k_trace_primary_ref<<<grid_for(n), kBlock, 0, s>>>(sc, job, d_id, d_t, d_ray, d_fetched, d_entered, d_tris);
@@ -808,33 +879,35 @@ void wf_trace_primary(const SceneDev& sc, const JobParams& job, int, int travers
     // FAST: the production persistent kernel over a scratch pool; "entered" reports replayed rays
     k_pack_primary<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, job, d_ray);
     k_reset_cursors<<<1, 32, 0, s>>>(ctl);
-    extend_fast<false>(scratch, sc, ctl, dims, reinterpret_cast<int*>(d_entered), s);
+    extend_fast<false>(scratch, sc, top, ctl, dims, reinterpret_cast<int*>(d_entered), s);
     k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_id, d_t);
     (void)d_fetched;
     (void)d_tris;
 }
 
 void wf_trace_closest(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_id, float* d_t,
-                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
+                      const TopPrims& top, const PoolView& scratch, Control* ctl, const LaunchDims& dims,
+                      cudaStream_t s) {
     if (traversal == TRT_TRAVERSE_REF) {
         k_trace_closest_ref<<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_id, d_t);
         return;
     }
     k_pack_rays<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, d_rays, n);
     k_reset_cursors<<<1, 32, 0, s>>>(ctl);
-    extend_fast<false>(scratch, sc, ctl, dims, nullptr, s);
+    extend_fast<false>(scratch, sc, top, ctl, dims, nullptr, s);
     k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_id, d_t);
 }
 
 void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ,
-                     const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s) {
+                     const TopPrims& top, const PoolView& scratch, Control* ctl, const LaunchDims& dims,
+                     cudaStream_t s) {
     if (traversal == TRT_TRAVERSE_REF) {
         k_trace_shadow_ref<<<grid_for(n), kBlock, 0, s>>>(sc, d_rays, n, d_occ);
         return;
     }
     k_pack_rays<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, d_rays, n);
     k_reset_cursors<<<1, 32, 0, s>>>(ctl);
-    shadow_fast<false>(scratch, sc, ctl, dims, s);
+    shadow_fast<false>(scratch, sc, top, ctl, dims, s);
     k_unpack_occluded<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_occ);
 }
 

@@ -69,7 +69,6 @@ struct LaunchDims {
     int fast_threads;   // threads of the persistent traversal CTAs (one CTA per SM): 512, 768 or 1024
     int smem_nodes;     // wide nodes staged into shared memory per CTA (top of the tree)
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
-    int tri_min;        // closest hit: lanes with a pending triangle needed to run the triangle step
 };
 
 // shared-memory bytes the persistent kernels need for a given configuration (0 = unsupported)
@@ -86,8 +85,9 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
 // one wavefront iteration (five kernels) on stream s
 // `marks`, when not null, receives five events recorded at the kernel boundaries of the
 // iteration: [prepare+regenerate] m1 [extend] m2 [shade] m3 [shadow] m4  (m0 first).
-void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const JobParams& job,
-                  int traversal, bool count, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks = nullptr);
+void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, cudaStream_t s,
+                  cudaEvent_t* marks = nullptr);
 // one-time opt-in to large dynamic shared memory for the persistent kernels
 int wf_configure();
 int wf_kernels_per_iteration(int traversal);
@@ -95,11 +95,12 @@ int wf_kernels_per_iteration(int traversal);
 // Parity / test entry points.  In FAST mode they run the production persistent kernels over a
 // scratch pool (`scratch`, capacity >= n rounded up to 256; `ctl` is the context's control block).
 void wf_trace_primary(const SceneDev& sc, const JobParams& job, int frame_seed, int traversal, int* d_id, float* d_t,
-                      float* d_ray, uint32_t* d_fetched, uint32_t* d_entered, uint32_t* d_tris,
+                      float* d_ray, uint32_t* d_fetched, uint32_t* d_entered, uint32_t* d_tris, const TopPrims& top,
                       const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s);
 void wf_trace_closest(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_id, float* d_t,
-                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s);
-void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ,
+                      const TopPrims& top, const PoolView& scratch, Control* ctl, const LaunchDims& dims,
+                      cudaStream_t s);
+void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ, const TopPrims& top,
                      const PoolView& scratch, Control* ctl, const LaunchDims& dims, cudaStream_t s);
 void wf_rng_states(const JobParams& job, int frame_local, int first_pixel, int n, uint32_t* d_states, cudaStream_t s);
 void wf_tonemap(const float* d_accum, int n_pixels, int frames, uint32_t* d_argb, cudaStream_t s);
