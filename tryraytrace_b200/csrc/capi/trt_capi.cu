@@ -74,7 +74,8 @@ struct trt_ctx {
 
     // XORWOW tables
     int rng_w = 0, rng_h = 0, n_col_bits = 0;
-    uint32_t* d_row_mats = nullptr;
+    uint32_t* d_row_a = nullptr;  // window tables of the row matrices (words 0-3 / word 4)
+    uint32_t* d_row_b = nullptr;
     uint32_t* d_col_pows = nullptr;
     XwColVec* d_col_vecs = nullptr;
     size_t col_vecs_cap = 0;
@@ -171,17 +172,22 @@ void pack_matrix(const Gf2Mat& m, uint32_t* dst) {  // 160 columns x 8 words
 
 int ensure_rng_tables(trt_ctx* c, int w, int h) {
     if (c->rng_w == w && c->rng_h == h) return 0;
-    cudaFree(c->d_row_mats);
+    cudaFree(c->d_row_a);
+    cudaFree(c->d_row_b);
     cudaFree(c->d_col_pows);
-    c->d_row_mats = c->d_col_pows = nullptr;
+    c->d_row_a = c->d_row_b = c->d_col_pows = nullptr;
     c->rng_w = c->rng_h = 0;
     std::vector<Gf2Mat> rows, cols;
     xorwow_build_row_matrices(w, h, rows);
     xorwow_build_col_powers(w, cols);
-    std::vector<uint32_t> packed((size_t)h * kXwMatWords);
-    for (int r = 0; r < h; r++) pack_matrix(rows[r], packed.data() + (size_t)r * kXwMatWords);
-    CU(cudaMalloc(&c->d_row_mats, packed.size() * 4));
-    CU(cudaMemcpyAsync(c->d_row_mats, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    std::vector<uint32_t> ta((size_t)h * kXwWindowEntries * 4), tb((size_t)h * kXwWindowEntries);
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < h; r++)
+        xorwow_window_table(rows[r], ta.data() + (size_t)r * kXwWindowEntries * 4, tb.data() + (size_t)r * kXwWindowEntries);
+    CU(cudaMalloc(&c->d_row_a, ta.size() * 4));
+    CU(cudaMalloc(&c->d_row_b, tb.size() * 4));
+    CU(cudaMemcpyAsync(c->d_row_a, ta.data(), ta.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_row_b, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice, c->stream));
     std::vector<uint32_t> pc(cols.size() * kXwMatWords);
     for (size_t j = 0; j < cols.size(); j++) pack_matrix(cols[j], pc.data() + j * kXwMatWords);
     CU(cudaMalloc(&c->d_col_pows, pc.size() * 4));
@@ -251,11 +257,11 @@ int ensure_scratch(trt_ctx* c, int n) {
     return 0;
 }
 
-// Launch configuration of the persistent traversal kernels.  Defaults from the B200 sweep
-// (profiles/): 768-thread CTAs (24 warps/SM at 80 registers), no node staging -- with the scene
-// L1-resident, staging the top of the tree into shared memory measured no faster than leaving
-// L1 to cache it, and the shared memory is better spent on stacks and ray queues.
-// TRT_FAST_THREADS / TRT_SMEM_NODES / TRT_REFILL override (tuning).
+// Launch configuration of the persistent traversal kernels.  Defaults from the B200 sweeps
+// (profiles/): 768-thread CTAs (24 warps/SM at 80 registers); whatever shared memory the stacks,
+// staging buffers and ray queues leave goes to the top of the tree (padded node staging);
+// phases of two node steps followed by triangle steps.
+// TRT_FAST_THREADS / TRT_SMEM_NODES / TRT_REFILL / TRT_PHASES override (tuning).
 LaunchDims launch_dims(const trt_ctx* c) {
     LaunchDims d;
     d.sms = c->sms;
@@ -265,10 +271,18 @@ LaunchDims launch_dims(const trt_ctx* c) {
         if (v == 512 || v == 768 || v == 1024) d.fast_threads = v;
     }
     const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
-    d.smem_nodes = 0;
+    d.smem_nodes = fit;
     if (const char* e = getenv("TRT_SMEM_NODES")) d.smem_nodes = std::max(0, std::min(fit, atoi(e)));
     d.refill_below = 25;
     if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
+    d.closest_phases = Phases{2, 16, 12};
+    d.shadow_phases = Phases{2, 16, 12};
+    if (const char* e = getenv("TRT_PHASES")) {  // "iters,node_min,tri_min[,iters,node_min,tri_min]" closest[,shadow]
+        int v[6] = {1, 33, 33, 1, 33, 33};
+        const int n = sscanf(e, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+        if (n >= 3) d.closest_phases = d.shadow_phases = Phases{std::max(1, v[0]), v[1], std::max(1, v[2])};
+        if (n >= 6) d.shadow_phases = Phases{std::max(1, v[3]), v[4], std::max(1, v[5])};
+    }
     return d;
 }
 
@@ -283,7 +297,8 @@ void fill_job(trt_ctx* c, JobParams& job, float* d_accum, int w, int h, int firs
     job.frame_stride = stride;
     job.seed_base = o.seed_base;
     job.n_frames = n_frames;
-    job.row_mats = c->d_row_mats;
+    job.row_a = reinterpret_cast<const uint4*>(c->d_row_a);
+    job.row_b = c->d_row_b;
     job.col_vecs = c->d_col_vecs;
     job.accum = d_accum;
 }
@@ -426,7 +441,8 @@ int trt_destroy(trt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c);
-    cudaFree(c->d_row_mats);
+    cudaFree(c->d_row_a);
+    cudaFree(c->d_row_b);
     cudaFree(c->d_col_pows);
     cudaFree(c->d_col_vecs);
     cudaFree(c->pool_mem);

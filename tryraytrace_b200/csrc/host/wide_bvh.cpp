@@ -2,6 +2,7 @@
 #include "wide_bvh.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <numeric>
@@ -34,9 +35,10 @@ struct BNode {
 };
 
 constexpr int kBins = 16;
-constexpr int kMaxLeaf = 4;
 constexpr float kCostBox = 1.0f;  // one child-box test
-constexpr float kCostTri = 1.3f;  // one triangle test
+// leaf policy (tuning knobs TRT_SAH_TRI / TRT_MAX_LEAF; defaults from the B200 sweep)
+int g_max_leaf = 4;
+float g_cost_tri = 2.5f;  // one triangle test, in child-box tests
 
 struct Builder {
     const std::vector<Box>& pbox;  // per object
@@ -103,10 +105,10 @@ struct Builder {
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = b; }
             }
         }
-        const float leaf_cost = kCostTri * count;
+        const float leaf_cost = g_cost_tri * count;
         const float split_cost =
-            best_axis < 0 ? INFINITY : 2.f * kCostBox + kCostTri * best_cost / std::max(box.area(), 1e-30f);
-        if (count <= kMaxLeaf && leaf_cost <= split_cost) return self;
+            best_axis < 0 ? INFINITY : 2.f * kCostBox + g_cost_tri * best_cost / std::max(box.area(), 1e-30f);
+        if (count <= g_max_leaf && leaf_cost <= split_cost) return self;
 
         int mid;
         if (best_axis < 0) {
@@ -168,6 +170,8 @@ void derived_leaf_box(const Object& o, float mn[3], float mx[3]) {
 
 void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* ref_nodes, int n_ref_nodes,
                     WideBvh& out) {
+    if (const char* e = getenv("TRT_SAH_TRI")) g_cost_tri = std::max(0.1f, (float)atof(e));
+    if (const char* e = getenv("TRT_MAX_LEAF")) g_max_leaf = std::max(1, std::min(4, atoi(e)));
     out.nodes.clear();
     out.tris.clear();
     out.leaf_boxes.assign(n_objects, LeafBox{{INFINITY, INFINITY, INFINITY, 0}, {-INFINITY, -INFINITY, -INFINITY, 0}});

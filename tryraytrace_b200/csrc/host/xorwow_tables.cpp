@@ -99,6 +99,20 @@ void xorwow_build_row_matrices(int w, int h, std::vector<Gf2Mat>& row_mats) {
     for (int r = 1; r < h; r++) gf2_matmul(step, row_mats[r - 1], row_mats[r]);
 }
 
+void xorwow_window_table(const Gf2Mat& m, uint32_t* a, uint32_t* b) {
+    for (int n = 0; n < 40; n++) {
+        for (int v = 0; v < 16; v++) {
+            uint32_t acc[5] = {0, 0, 0, 0, 0};
+            for (int bit = 0; bit < 4; bit++)
+                if ((v >> bit) & 1)
+                    for (int k = 0; k < 5; k++) acc[k] ^= m.col[4 * n + bit][k];
+            const int e = n * 16 + v;
+            for (int k = 0; k < 4; k++) a[e * 4 + k] = acc[k];
+            b[e] = acc[4];
+        }
+    }
+}
+
 void xorwow_build_col_powers(int w, std::vector<Gf2Mat>& col_pows) {
     int bits = 1;
     while ((1 << bits) < w) bits++;

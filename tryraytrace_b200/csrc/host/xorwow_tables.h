@@ -48,4 +48,11 @@ void xorwow_init_host(uint64_t seed, uint64_t subsequence, uint32_t v[5], uint32
 void xorwow_build_row_matrices(int w, int h, std::vector<Gf2Mat>& row_mats);
 void xorwow_build_col_powers(int w, std::vector<Gf2Mat>& col_pows);
 
+// 4-bit window form of a matrix for the device mat-vec (kernels/xorwow.cuh): the 160 input
+// bits are cut into 40 nibbles; entry [n][v] is the XOR of the columns selected by the bits of
+// v in nibble n, so a mat-vec is 40 table lookups instead of 160 conditional XORs.  Words 0-3
+// go to `a` (16 B per entry), word 4 to `b`; 640 entries per matrix each.
+constexpr int kXwWindowEntriesHost = 40 * 16;
+void xorwow_window_table(const Gf2Mat& m, uint32_t* a /* 640 x 4 words */, uint32_t* b /* 640 words */);
+
 }  // namespace trt

@@ -20,8 +20,15 @@
 //     otherwise (kTriNoDerive), which forces the replay below.
 //  4. Ambiguity.  The only order-dependent case left is a candidate whose leaf-box entry is not
 //     below its own hit distance (the reference culls against the running d_min, which depends
-//     on visit order).  Such rays are flagged and re-run through TRAVERSE_REF.  Ties in t resolve
-//     to the lowest object index, as the reference's ascending leaf order does.
+//     on visit order).  Such rays are re-run through TRAVERSE_REF.  Ties in t resolve to the
+//     lowest object index, as the reference's ascending leaf order does.
+//  5. Deferred verification.  (3) and (4) only matter for the FINAL winner w = the candidate with
+//     the smallest t (lowest id on ties) over the superset: the reference's running d_min never
+//     drops below t_w (every triangle it can accept is a candidate here), so if w's leaf box
+//     passes with entry < t_w all of w's ancestors pass whenever the reference visits them, w is
+//     tested, and nothing tested beats it.  So candidates are accepted on the triangle test
+//     alone while traversing, and the leaf-box reach of the winner is checked once per ray; if
+//     it fails (FP corner cases, or a box that cannot be re-derived) the ray is replayed.
 // Any-hit queries have a fixed interval, so (3) decides them exactly and no replay exists.
 //
 // Execution model (kernels in wavefront.cu).  One persistent CTA per SM.  Two levels:
@@ -33,8 +40,9 @@
 //   * TREE PHASE.  Rays that enter the tree are compacted (__ballot_sync/__popc) into a per-warp
 //     queue in shared memory, carrying the d_min / id found so far; idle traversal lanes refill
 //     from that queue.
-// The tree traversal is written as ROUNDS so the lanes stay converged: in every round a lane performs
-// at most one wide-node step (four child-box tests) and at most one triangle step.  Inner
+// The tree traversal is speculative while-while (Aila & Laine 2009) in warp-converged PHASES:
+// a few node steps (four child-box tests each, packed FADD2/FMUL2), then triangle steps for the
+// leaves that piled up meanwhile, so triangle tests run with fuller warps.  Inner
 // children go to a per-lane node stack, leaf children to a separate per-lane triangle stack;
 // both live in SHARED memory (lane-interleaved, conflict free), with a local-memory overflow
 // that only deep trees ever touch.  The top of the tree (the first k nodes, emitted by the
@@ -52,6 +60,7 @@ struct WideCounts {
 };
 
 constexpr int kWideEmptyRef = 0x7fffffff;
+constexpr int kSmemNodeStride = 144;  // bytes between staged nodes in shared memory (128 + 16 pad)
 constexpr int kSpillEntries = 48;  // logical node stack bound: 3 * wide depth + 1 (checked at upload)
 constexpr float kCullSlack = 1.0005f;
 constexpr int kTriIdMask = 0x3fffffff;
@@ -112,6 +121,69 @@ TRT_DEV uint32_t lds32(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
+}
+
+// Both pushes of one child in a single predicated sequence: the leaf push (triangle stack,
+// grows down) when `hit && ref < 0`, the inner push (node stack, grows up) when the child's key
+// is valid and not the one kept in a register.  np / tp are bumped in place under the same
+// predicates, so a child costs nine instructions and no branch.
+template <uint32_t E>
+TRT_DEV void push_child(uint32_t& np, uint32_t& tp, float tn, float tf, int ref, unsigned key, unsigned best) {
+    asm volatile(
+        "{\n\t.reg .pred pt, pn;\n\t.reg .b32 nref;\n\t"
+        "setp.le.ftz.f32 pt, %2, %3;\n\t"
+        "setp.lt.and.s32 pt, %4, 0, pt;\n\t"
+        "setp.ne.u32 pn, %5, %6;\n\t"
+        "setp.ne.and.u32 pn, %5, 0xffffffff, pn;\n\t"
+        "not.b32 nref, %4;\n\t"
+        "@pt st.shared.v2.b32 [%1], {%7, nref};\n\t"
+        "@pt sub.u32 %1, %1, %8;\n\t"
+        "@pn st.shared.v2.b32 [%0], {%7, %4};\n\t"
+        "@pn add.u32 %0, %0, %8;\n\t}"
+        : "+r"(np), "+r"(tp)
+        : "f"(tn), "f"(tf), "r"(ref), "r"(key), "r"(best), "r"(__float_as_uint(tn)), "n"(E));
+}
+// any hit: 32-bit entries, no distances, every hit inner child is pushed
+template <uint32_t E>
+TRT_DEV void push_child_any(uint32_t& np, uint32_t& tp, float tn, float tf, int ref) {
+    asm volatile(
+        "{\n\t.reg .pred h, pt, pn;\n\t.reg .b32 nref;\n\t"
+        "setp.le.ftz.f32 h, %2, %3;\n\t"
+        "setp.lt.and.s32 pt, %4, 0, h;\n\t"
+        "setp.ge.and.s32 pn, %4, 0, h;\n\t"
+        "not.b32 nref, %4;\n\t"
+        "@pt st.shared.b32 [%1], nref;\n\t"
+        "@pt sub.u32 %1, %1, %5;\n\t"
+        "@pn st.shared.b32 [%0], %4;\n\t"
+        "@pn add.u32 %0, %0, %5;\n\t}"
+        : "+r"(np), "+r"(tp)
+        : "f"(tn), "f"(tf), "r"(ref), "n"(E));
+}
+
+// Packed FP32 (sm_100 FADD2 / FMUL2): two lanes of the same rn/ftz operation per instruction,
+// each lane rounded exactly like the scalar op, so the slab arithmetic below is bit-identical
+// to (plane - o) * inv evaluated per child.
+TRT_DEV float2 sub2(float2 a, float s) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+        "sub.rn.ftz.f32x2 rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(s));
+    return r;
+}
+TRT_DEV float2 mul2(float2 a, float s) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+        "mul.rn.ftz.f32x2 rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(s));
+    return r;
+}
+// (plane - o) * inv for the four children of one plane vector
+TRT_DEV float4 plane_t(float4 p, float o, float inv) {
+    const float2 a = mul2(sub2(make_float2(p.x, p.y), o), inv);
+    const float2 b = mul2(sub2(make_float2(p.z, p.w), o), inv);
+    return make_float4(a.x, a.y, b.x, b.y);
 }
 
 // streaming (evict-first) stores for results that are read once by the next kernel
@@ -191,7 +263,10 @@ struct NodeData {
 TRT_DEV void load_node(NodeData& n, const unsigned char* s_nodes, int k_smem, const float4* g_nodes, int node, int nxo,
                        int nyo, int nzo) {
     if (node < k_smem) {
-        const unsigned char* b = s_nodes + node * 128;
+        // staged nodes sit 144 bytes apart: the 16-byte plane vector a lane reads then falls into
+        // bank group (node + k) mod 8, so the lanes of a warp (all reading the same k of different
+        // nodes) spread over the banks instead of colliding on one group
+        const unsigned char* b = s_nodes + node * kSmemNodeStride;
         n.nx = *reinterpret_cast<const float4*>(b + nxo);
         n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
         n.ny = *reinterpret_cast<const float4*>(b + nyo);
@@ -223,11 +298,12 @@ struct ClosestRay {
     int nxo, nyo, nzo;  // near-plane byte offsets (see load_node)
     uint32_t np, tp;    // shared-window addresses of the next free node / triangle entry
     int nspill;         // entries in the local overflow
-    bool amb;
+    int win;            // where the current winner came from: >= 0 triangle record index in the tree,
+                        // -1 none, -2 - p root-level primitive p (its leaf box is verified at the end)
 };
 
 // Tree-phase entry: the ray with the d_min / id / ambiguity the top phase found.
-TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, float d_min, int id, bool amb,
+TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, float d_min, int id, int win,
                            uint32_t base, uint32_t ttop) {
     s.o = f3(o4.x, o4.y, o4.z);
     s.d = f3(d4.x, d4.y, d4.z);
@@ -237,20 +313,20 @@ TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, floa
     s.nzo = s.inv.z < 0.f ? 80 : 64;
     s.d_min = d_min;
     s.id = id;
-    s.amb = amb;
+    s.win = win;
     s.np = base;
     s.tp = ttop;
     s.nspill = 0;
     s.cur = 0;  // root
 }
 
-// TOP PHASE, closest hit: the root-level list, brute force, same accept rule as the tree phase
-// (exact triangle arithmetic, exact leaf-box reach, lowest id on ties, ambiguity flag), then the
-// tree's bounding box against [0, d_min].  Every lane of the warp runs this for its own ray.
+// TOP PHASE, closest hit: the root-level list, brute force, same triangle arithmetic and tie rule
+// as the tree phase, then the tree's bounding box against [0, d_min].  Every lane of the warp
+// runs this for its own ray.
 struct TopResult {
     float d_min;
     int id;
-    bool amb;
+    int win;      // -1 none, -2 - p
     bool enters;  // the ray can reach something in the tree
 };
 TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
@@ -259,17 +335,16 @@ TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
     TopResult r;
     r.d_min = 1e20f;
     r.id = -1;
-    r.amb = false;
+    r.win = -1;
 #pragma unroll 1
     for (int p = 0; p < top.n; p++) {
         const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
         const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
         const int tid = f2i(a.w);
-        float entry;
-        const bool reach = leaf_box_reach(top.bmin[p], top.bmax[p], o, inv, sx, sy, sz, &entry);
-        if (reach && t > 0.f && (t < r.d_min || (t == r.d_min && tid < r.id))) {
-            if (entry < t) { r.d_min = t; r.id = tid; }
-            else r.amb = true;
+        if (t > 0.f && (t < r.d_min || (t == r.d_min && tid < r.id))) {
+            r.d_min = t;
+            r.id = tid;
+            r.win = -2 - p;
         }
     }
     float tn;
@@ -281,19 +356,47 @@ TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
     return r;
 }
 
-// One round for one lane; called by ALL lanes of the warp (a lane without a ray has empty stacks
-// and nothing happens for it).  E = bytes between consecutive entries of this lane, S = entries.
-template <uint32_t E, int S, bool COUNT>
-TRT_DEV bool closest_round(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ClosestRay& s, uint32_t base,
-                           uint2* spill, WideCounts* wc) {
-    const uint32_t ttop = base + (S - 1) * E;
-    const float limit = s.d_min * kCullSlack;
+// Deferred verification of a ray's winner (exactness argument, point 5): its reference leaf box
+// must pass the reference's slab test with an entry below the hit distance.
+TRT_DEV bool verify_winner(const SceneDev& sc, const TopPrims& top, const F3 o, const F3 d, int win, float t) {
+    if (win == -1) return true;  // a miss is a miss
+    float4 bmin, bmax;
+    if (win >= 0) {
+        const float4* tp = sc.tris + (size_t)win * 3;
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+        if (f2i(ta.w) & kTriNoDerive) return false;
+        derive_leaf_box(f3(ta.x, ta.y, ta.z), f3(tb.x, tb.y, tb.z), f3(tc.x, tc.y, tc.z), &bmin, &bmax);
+    } else {
+        bmin = top.bmin[-2 - win];
+        bmax = top.bmax[-2 - win];
+    }
+    const F3 inv = f3(ref_safe_inv(d.x), ref_safe_inv(d.y), ref_safe_inv(d.z));
+    float entry;
+    return leaf_box_reach(bmin, bmax, o, inv, inv.x < 0.f, inv.y < 0.f, inv.z < 0.f, &entry) && entry < t;
+}
+
+// The traversal of one lane is cut into NODE steps and TRIANGLE steps; the kernels run them in
+// phases (several node steps, then triangle steps) with all lanes of the warp taking part -- a
+// lane without work of a kind falls through.  E = bytes between consecutive stack entries of
+// this lane, S = entries per lane.
+template <uint32_t E, int S>
+TRT_DEV bool closest_has_room(const ClosestRay& s) {
     // at least four free entries (a node step can push that many); tp - np = (free - 1) * E, signed:
     // a completely full stack gives -E
-    const bool room = (int)(s.tp - s.np) >= (int)(3 * E);
-    // ---- choose this round's node: the held one, else the nearest-first stack --------------
+    return (int)(s.tp - s.np) >= (int)(3 * E);
+}
+TRT_DEV bool closest_node_work(const ClosestRay& s, uint32_t base) {
+    return s.cur != kWideEmptyRef || s.np != base || s.nspill > 0;
+}
+
+template <uint32_t E, int S, bool COUNT>
+TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ClosestRay& s,
+                               uint32_t base, uint2* spill, WideCounts* wc) {
+    const uint32_t ttop = base + (S - 1) * E;
+    const float limit = s.d_min * kCullSlack;
+    // ---- choose the node: the held one, else the nearest-first stack --------------------------
     int node = kWideEmptyRef;
-    if (room) {
+    if (closest_has_room<E, S>(s)) {
         node = s.cur;
         s.cur = kWideEmptyRef;
         if (node == kWideEmptyRef) {
@@ -315,7 +418,38 @@ TRT_DEV bool closest_round(const unsigned char* s_nodes, int k_smem, const Scene
         for (uint32_t a = base; a != s.np; a += E) spill[s.nspill++] = lds64(a);
         s.np = base;
     }
-    // ---- choose this round's triangle -------------------------------------------------------
+    if (node == kWideEmptyRef) return;
+    if (COUNT) wc->nodes++;
+    NodeData n;
+    load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    // slab intervals of the four children, packed two per instruction
+    const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
+    const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
+    const float4 az = plane_t(n.nz, s.o.z, s.inv.z), bz = plane_t(n.fz, s.o.z, s.inv.z);
+    float tn[4], tf[4];
+    tn[0] = fmaxf(fmaxf(ax.x, ay.x), fmaxf(az.x, 0.f)); tf[0] = fminf(fminf(bx.x, by.x), fminf(bz.x, limit));
+    tn[1] = fmaxf(fmaxf(ax.y, ay.y), fmaxf(az.y, 0.f)); tf[1] = fminf(fminf(bx.y, by.y), fminf(bz.y, limit));
+    tn[2] = fmaxf(fmaxf(ax.z, ay.z), fmaxf(az.z, 0.f)); tf[2] = fminf(fminf(bx.z, by.z), fminf(bz.z, limit));
+    tn[3] = fmaxf(fmaxf(ax.w, ay.w), fmaxf(az.w, 0.f)); tf[3] = fminf(fminf(bx.w, by.w), fminf(bz.w, limit));
+    const int r[4] = {n.ch.x, n.ch.y, n.ch.z, n.ch.w};
+    // nearest inner child stays in a register: entry distances are >= 0, so their bit patterns
+    // order like the floats; the child slot rides in the two low mantissa bits
+    unsigned key[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        key[k] = (tn[k] <= tf[k] && r[k] >= 0) ? ((__float_as_uint(tn[k]) & ~3u) | (unsigned)k) : 0xffffffffu;
+    const unsigned best = min(min(key[0], key[1]), min(key[2], key[3]));
+    const int r01 = (best & 1u) ? r[1] : r[0], r23 = (best & 1u) ? r[3] : r[2];
+    const int rb = (best & 2u) ? r23 : r01;
+    s.cur = best != 0xffffffffu ? rb : kWideEmptyRef;
+#pragma unroll
+    for (int k = 0; k < 4; k++) push_child<E>(s.np, s.tp, tn[k], tf[k], r[k], key[k], best);
+}
+
+template <uint32_t E, int S, bool COUNT>
+TRT_DEV void closest_tri_step(const SceneDev& sc, ClosestRay& s, uint32_t base, WideCounts* wc) {
+    const uint32_t ttop = base + (S - 1) * E;
+    const float limit = s.d_min * kCullSlack;
     int tri = -1;
     while (s.tp != ttop) {
         const uint32_t top = s.tp + E;
@@ -328,63 +462,23 @@ TRT_DEV bool closest_round(const unsigned char* s_nodes, int k_smem, const Scene
         if (!more) s.tp = top;
         break;
     }
-    // ---- node step ----------------------------------------------------------------------------
-    if (node != kWideEmptyRef) {
-        if (COUNT) wc->nodes++;
-        NodeData n;
-        load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
-        float t[4];
-        bool h[4];
-        h[0] = child_interval(n.nx.x, n.fx.x, n.ny.x, n.fy.x, n.nz.x, n.fz.x, s.o, s.inv, 0.f, limit, &t[0]);
-        h[1] = child_interval(n.nx.y, n.fx.y, n.ny.y, n.fy.y, n.nz.y, n.fz.y, s.o, s.inv, 0.f, limit, &t[1]);
-        h[2] = child_interval(n.nx.z, n.fx.z, n.ny.z, n.fy.z, n.nz.z, n.fz.z, s.o, s.inv, 0.f, limit, &t[2]);
-        h[3] = child_interval(n.nx.w, n.fx.w, n.ny.w, n.fy.w, n.nz.w, n.fz.w, s.o, s.inv, 0.f, limit, &t[3]);
-        const int r[4] = {n.ch.x, n.ch.y, n.ch.z, n.ch.w};
-        // nearest inner child stays in a register: entry distances are >= 0, so their bit
-        // patterns order like the floats; the child slot rides in the two low mantissa bits
-        unsigned key[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            key[k] = (h[k] && r[k] >= 0) ? ((__float_as_uint(t[k]) & ~3u) | (unsigned)k) : 0xffffffffu;
-        const unsigned best = min(min(key[0], key[1]), min(key[2], key[3]));
-        const int r01 = (best & 1u) ? r[1] : r[0], r23 = (best & 1u) ? r[3] : r[2];
-        const int rb = (best & 2u) ? r23 : r01;
-        s.cur = best != 0xffffffffu ? rb : kWideEmptyRef;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const bool leaf = r[k] < 0;
-            const bool push_tri = h[k] && leaf;
-            const bool push_node = h[k] && !leaf && key[k] != best;
-            const uint32_t tb = __float_as_uint(t[k]);
-            sts64_if(push_tri, s.tp, tb, (uint32_t)(~r[k]));
-            sts64_if(push_node, s.np, tb, (uint32_t)r[k]);
-            s.tp -= push_tri ? E : 0u;
-            s.np += push_node ? E : 0u;
-        }
+    if (tri < 0) return;
+    if (COUNT) wc->tris++;
+    const float4* tp = sc.tris + (size_t)tri * 3;
+    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+    const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
+    const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
+    const int tid = f2i(ta.w) & kTriIdMask;
+    if (t > 0.f && (t < s.d_min || (t == s.d_min && tid < s.id))) {
+        s.d_min = t;  // accepted on the triangle test alone; the winner is verified once per ray
+        s.id = tid;
+        s.win = tri;
     }
-    // ---- triangle step ------------------------------------------------------------------------
-    if (tri >= 0) {
-        if (COUNT) wc->tris++;
-        const float4* tp = sc.tris + (size_t)tri * 3;
-        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-        const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
-        const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
-        const int code = f2i(ta.w);
-        const int tid = code & kTriIdMask;
-        if (t > 0.f && (t < s.d_min || (t == s.d_min && tid < s.id))) {
-            // would the reference traversal have reached this triangle?
-            float4 bmin, bmax;
-            derive_leaf_box(v0, v1, v2, &bmin, &bmax);
-            float entry;
-            if (code & kTriNoDerive) {
-                s.amb = true;
-            } else if (leaf_box_reach(bmin, bmax, s.o, s.inv, s.nxo != 0, s.nyo != 32, s.nzo != 64, &entry)) {
-                if (entry < t) { s.d_min = t; s.id = tid; }
-                else s.amb = true;  // reach depends on the reference's visit order: replay
-            }
-        }
-    }
-    return s.cur == kWideEmptyRef && s.np == base && s.tp == ttop && s.nspill == 0;  // done
+}
+
+template <uint32_t E, int S>
+TRT_DEV bool closest_done(const ClosestRay& s, uint32_t base) {
+    return s.cur == kWideEmptyRef && s.np == base && s.tp == base + (S - 1) * E && s.nspill == 0;
 }
 
 // ---- any hit -----------------------------------------------------------------------------------
@@ -416,7 +510,9 @@ TRT_DEV void shadow_begin(ShadowRay& s, const float4 o4, const float4 d4, uint32
 }
 
 // TOP PHASE, any hit: returns 1 = occluded by a root-level primitive, 2 = must traverse the tree,
-// 0 = unoccluded.  Same exact tests as the tree phase.
+// 0 = unoccluded.  Same exact tests as the tree phase; the leaf-box test of a primitive is only
+// evaluated when some lane of the warp actually has a triangle hit inside its interval (walls
+// almost never shadow a ray that stays inside the room).  Called by all lanes of a warp.
 TRT_DEV int top_shadow(const TopPrims& top, const F3 o, const F3 d, float max_dist) {
     const F3 inv = f3(p_rcp(d.x), p_rcp(d.y), p_rcp(d.z));  // raw reciprocal, reference :276
     const float t_hi = p_sub(max_dist, 0.001f);
@@ -425,8 +521,10 @@ TRT_DEV int top_shadow(const TopPrims& top, const F3 o, const F3 d, float max_di
     for (int p = 0; p < top.n; p++) {
         const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
         const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
-        const bool reach = ref_slab(top.bmin[p], top.bmax[p], o, inv, 0.001f, max_dist);
-        occluded = occluded || (t > 0.001f && t < t_hi && reach);
+        const bool hit = t > 0.001f && t < t_hi;
+        if (__any_sync(0xffffffffu, hit)) {
+            if (hit && ref_slab(top.bmin[p], top.bmax[p], o, inv, 0.001f, max_dist)) occluded = true;
+        }
     }
     if (occluded) return 1;
     float tn;
@@ -438,12 +536,19 @@ TRT_DEV int top_shadow(const TopPrims& top, const F3 o, const F3 d, float max_di
     return enters ? 2 : 0;
 }
 
+template <uint32_t E, int S>
+TRT_DEV bool shadow_has_room(const ShadowRay& s) { return (int)(s.tp - s.np) >= (int)(3 * E); }
+TRT_DEV bool shadow_node_work(const ShadowRay& s, uint32_t base) {
+    return !s.occluded && (s.np != base || s.nspill > 0);
+}
+
 template <uint32_t E, int S, bool COUNT>
-TRT_DEV bool shadow_round(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ShadowRay& s, uint32_t base,
-                          uint32_t* spill, WideCounts* wc) {
+TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ShadowRay& s,
+                              uint32_t base, uint32_t* spill, WideCounts* wc) {
     const uint32_t ttop = base + (S - 1) * E;
     int node = kWideEmptyRef;
-    if ((int)(s.tp - s.np) >= (int)(3 * E)) {
+    if (s.occluded) return;
+    if (shadow_has_room<E, S>(s)) {
         if (s.np != base) {
             s.np -= E;
             node = (int)lds32(s.np);
@@ -455,63 +560,58 @@ TRT_DEV bool shadow_round(const unsigned char* s_nodes, int k_smem, const SceneD
         for (uint32_t a = base; a != s.np; a += E) spill[s.nspill++] = lds32(a);
         s.np = base;
     }
-    int tri = -1;
-    if (s.tp != ttop) {
-        const uint32_t top = s.tp + E;
-        const int code = (int)lds32(top);
-        tri = code >> 2;
-        const bool more = (code & 3) != 0;
-        sts32_if(more, top, (uint32_t)(code + 3));
-        if (!more) s.tp = top;
-    }
-    if (node != kWideEmptyRef) {
-        if (COUNT) wc->nodes++;
-        NodeData n;
-        load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
-        float t;
-        bool h[4];
-        // the reference's box interval for shadow rays is (0.001, max_dist)
-        h[0] = child_interval(n.nx.x, n.fx.x, n.ny.x, n.fy.x, n.nz.x, n.fz.x, s.o, s.inv, 0.001f, s.max_dist, &t);
-        h[1] = child_interval(n.nx.y, n.fx.y, n.ny.y, n.fy.y, n.nz.y, n.fz.y, s.o, s.inv, 0.001f, s.max_dist, &t);
-        h[2] = child_interval(n.nx.z, n.fx.z, n.ny.z, n.fy.z, n.nz.z, n.fz.z, s.o, s.inv, 0.001f, s.max_dist, &t);
-        h[3] = child_interval(n.nx.w, n.fx.w, n.ny.w, n.fy.w, n.nz.w, n.fz.w, s.o, s.inv, 0.001f, s.max_dist, &t);
-        const int r[4] = {n.ch.x, n.ch.y, n.ch.z, n.ch.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const bool leaf = r[k] < 0;
-            const bool push_tri = h[k] && leaf;
-            const bool push_node = h[k] && !leaf;
-            sts32_if(push_tri, s.tp, (uint32_t)(~r[k]));
-            sts32_if(push_node, s.np, (uint32_t)r[k]);
-            s.tp -= push_tri ? E : 0u;
-            s.np += push_node ? E : 0u;
+    if (node == kWideEmptyRef) return;
+    if (COUNT) wc->nodes++;
+    NodeData n;
+    load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
+    const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
+    const float4 az = plane_t(n.nz, s.o.z, s.inv.z), bz = plane_t(n.fz, s.o.z, s.inv.z);
+    // the reference's box interval for shadow rays is (0.001, max_dist)
+    const float lo = 0.001f, hi = s.max_dist;
+    push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.x, ay.x), fmaxf(az.x, lo)), fminf(fminf(bx.x, by.x), fminf(bz.x, hi)), n.ch.x);
+    push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.y, ay.y), fmaxf(az.y, lo)), fminf(fminf(bx.y, by.y), fminf(bz.y, hi)), n.ch.y);
+    push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.z, ay.z), fmaxf(az.z, lo)), fminf(fminf(bx.z, by.z), fminf(bz.z, hi)), n.ch.z);
+    push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.w, ay.w), fmaxf(az.w, lo)), fminf(fminf(bx.w, by.w), fminf(bz.w, hi)), n.ch.w);
+}
+
+template <uint32_t E, int S, bool COUNT>
+TRT_DEV void shadow_tri_step(const SceneDev& sc, ShadowRay& s, uint32_t base, WideCounts* wc) {
+    const uint32_t ttop = base + (S - 1) * E;
+    if (s.occluded || s.tp == ttop) return;
+    const uint32_t top = s.tp + E;
+    const int scode = (int)lds32(top);
+    const int tri = scode >> 2;
+    const bool more = (scode & 3) != 0;
+    sts32_if(more, top, (uint32_t)(scode + 3));
+    if (!more) s.tp = top;
+    if (COUNT) wc->tris++;
+    const float4* tp = sc.tris + (size_t)tri * 3;
+    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+    const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
+    const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
+    if (t > 0.001f && t < s.t_hi) {
+        const int code = f2i(ta.w);
+        bool reach;
+        if (code & kTriNoDerive) {
+            // leaf box not derivable: ask the reference traversal itself (exact, rare)
+            Ray r;
+            r.o = s.o;
+            r.d = s.d;
+            VisitCounts vc = {0, 0, 0};
+            reach = ref_shadow<false>(sc, r, s.max_dist, &vc);
+        } else {
+            float4 bmin, bmax;
+            derive_leaf_box(v0, v1, v2, &bmin, &bmax);
+            reach = ref_slab(bmin, bmax, s.o, s.inv, 0.001f, s.max_dist);
         }
+        if (reach) s.occluded = true;
     }
-    if (tri >= 0) {
-        if (COUNT) wc->tris++;
-        const float4* tp = sc.tris + (size_t)tri * 3;
-        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-        const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
-        const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
-        if (t > 0.001f && t < s.t_hi) {
-            const int code = f2i(ta.w);
-            bool reach;
-            if (code & kTriNoDerive) {
-                // leaf box not derivable: ask the reference traversal itself (exact, rare)
-                Ray r;
-                r.o = s.o;
-                r.d = s.d;
-                VisitCounts vc = {0, 0, 0};
-                reach = ref_shadow<false>(sc, r, s.max_dist, &vc);
-            } else {
-                float4 bmin, bmax;
-                derive_leaf_box(v0, v1, v2, &bmin, &bmax);
-                reach = ref_slab(bmin, bmax, s.o, s.inv, 0.001f, s.max_dist);
-            }
-            if (reach) s.occluded = true;
-        }
-    }
-    return s.occluded || (s.np == base && s.tp == ttop && s.nspill == 0);  // done
+}
+
+template <uint32_t E, int S>
+TRT_DEV bool shadow_done(const ShadowRay& s, uint32_t base) {
+    return s.occluded || (s.np == base && s.tp == base + (S - 1) * E && s.nspill == 0);
 }
 
 }  // namespace trt

@@ -114,14 +114,14 @@ __global__ void k_col_table(const uint32_t* __restrict__ col_pows, int n_col_bit
     out[i] = e;
 }
 
-// RNG state of (job-local frame f, pixel) = row_mats[row] * col_vecs[f][col]
+// RNG state of (job-local frame f, pixel) = M^(w*row) * col_vecs[f][col]
 TRT_DEV Xorwow sample_rng(const JobParams& job, int f, int row, int col) {
     const XwColVec* cv = job.col_vecs + (size_t)f * job.rc.width + col;
     const uint4 a = __ldg(reinterpret_cast<const uint4*>(cv));
     const uint2 b = __ldg(reinterpret_cast<const uint2*>(cv) + 2);
     const uint32_t in[5] = {a.x, a.y, a.z, a.w, b.x};
     uint32_t o[5];
-    xw_matvec(job.row_mats + (size_t)row * kXwMatWords, in, o);
+    xw_matvec_window(job.row_a + (size_t)row * kXwWindowEntries, job.row_b + (size_t)row * kXwWindowEntries, in, o);
     Xorwow s;
     s.v0 = o[0]; s.v1 = o[1]; s.v2 = o[2]; s.v3 = o[3]; s.v4 = o[4];
     s.d = b.y;
@@ -382,19 +382,19 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
 template <int THREADS, bool COUNT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
-              int refill_below, int* amb_out) {
+              int refill_below, Phases ph, int* amb_out) {
     constexpr int S = FastCfg<THREADS>::SC;
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_nodes = smem;
-    uint2* s_stack = reinterpret_cast<uint2*>(smem + (size_t)k_smem * 128);
+    uint2* s_stack = reinterpret_cast<uint2*>(smem + (size_t)k_smem * kSmemNodeStride);
     float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
     unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
-        reinterpret_cast<float4*>(s_nodes)[i] = __ldg(sc.wide_nodes + i);
+        reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
     if (lane == 0) {
         mbar_init(&s_bars[warp * 2], 1);
         mbar_init(&s_bars[warp * 2 + 1], 1);
@@ -405,7 +405,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
     uint64_t* bars = s_bars + warp * 2;
     float4* q_o = reinterpret_cast<float4*>(s_queue + warp * kQueueBytesClosest);  // origin, d_min
-    float4* q_d = q_o + kQueueCap;                                                  // direction, (id + 1) | amb << 31
+    float4* q_d = q_o + kQueueCap;                                                  // direction, winner so far (-1 / -2 - p)
     int* q_s = reinterpret_cast<int*>(q_d + kQueueCap);                             // pool slot
     constexpr uint32_t E = THREADS * 8;  // bytes between consecutive stack entries of one lane
     const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
@@ -437,23 +437,25 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             TopResult tr = top_closest(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
             if (live) rays++;
             if (live && !tr.enters) {  // decided by the root-level list alone
-                if (tr.amb) {  // rare: order-dependent reach, re-run in reference order
+                const F3 ro = f3(o4.x, o4.y, o4.z), rd = f3(d4.x, d4.y, d4.z);
+                const bool ok = verify_winner(sc, top, ro, rd, tr.win, tr.d_min);
+                if (!ok) {  // rare: order-dependent reach, re-run in reference order
                     Ray r;
-                    r.o = f3(o4.x, o4.y, o4.z);
-                    r.d = f3(d4.x, d4.y, d4.z);
+                    r.o = ro;
+                    r.d = rd;
                     VisitCounts vc = {0, 0, 0};
                     tr.id = ref_closest<false>(sc, r, &tr.d_min, &vc);
                     replays++;
                 }
                 st_cs_f2(&pool.hit[my_slot], make_float2(tr.d_min, i2f(tr.id)));
-                if (amb_out) amb_out[my_slot] = tr.amb ? 1 : 0;
+                if (amb_out) amb_out[my_slot] = ok ? 0 : 1;
             }
             const bool tree = live && tr.enters;
             const unsigned m = __ballot_sync(0xffffffffu, tree);
             if (tree) {
                 const int qi = qn + __popc(m & lt_mask);
                 q_o[qi] = make_float4(o4.x, o4.y, o4.z, tr.d_min);
-                q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f((tr.id + 1) | (tr.amb ? (int)0x80000000 : 0)));
+                q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f(tr.win));
                 q_s[qi] = my_slot;
             }
             qn += __popc(m);
@@ -467,8 +469,8 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             if (!has && rank < qn) {
                 const int qi = qn - 1 - rank;
                 const float4 o4 = q_o[qi], d4 = q_d[qi];
-                const int code = f2i(d4.w);
-                closest_begin(st, o4, d4, o4.w, (code & 0x7fffffff) - 1, code < 0, stk_base, stk_ttop);
+                const int win = f2i(d4.w);  // -1 or a root-level primitive
+                closest_begin(st, o4, d4, o4.w, win == -1 ? -1 : f2i(top.v0[-2 - win].w), win, stk_base, stk_ttop);
                 slot = q_s[qi];
                 has = true;
             }
@@ -480,11 +482,26 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             if (qn == 0 && feeder_exhausted(fd)) break;
             continue;
         }
-        // 3. one traversal round; every lane takes part (a lane without a ray has empty stacks)
-        if (closest_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc) && has) {
+        // 3. node phase: up to `node_iters` node steps, while enough lanes still have node work
+#pragma unroll 1
+        for (int it = 0; it < ph.node_iters; it++) {
+            closest_node_step<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
+            const unsigned m = __ballot_sync(0xffffffffu, closest_node_work(st, stk_base) && closest_has_room<E, S>(st));
+            if (__popc(m) < ph.node_min) break;
+        }
+        // 4. triangle phase: at least one step, more while enough lanes have a triangle waiting
+#pragma unroll 1
+        for (;;) {
+            closest_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
+            const unsigned m = __ballot_sync(0xffffffffu, st.tp != stk_ttop);
+            if (__popc(m) < ph.tri_min) break;
+        }
+        // 5. finished rays write their hit
+        if (has && closest_done<E, S>(st, stk_base)) {
             float t = st.d_min;
             int id = st.id;
-            if (st.amb) {  // rare: order-dependent reach, re-run in reference order
+            const bool ok = verify_winner(sc, top, st.o, st.d, st.win, t);
+            if (!ok) {  // rare: order-dependent reach, re-run in reference order
                 Ray r;
                 r.o = st.o;
                 r.d = st.d;
@@ -493,7 +510,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
                 replays++;
             }
             st_cs_f2(&pool.hit[slot], make_float2(t, i2f(id)));
-            if (amb_out) amb_out[slot] = st.amb ? 1 : 0;
+            if (amb_out) amb_out[slot] = ok ? 0 : 1;
             has = false;
         }
     }
@@ -510,19 +527,19 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
 template <int THREADS, bool COUNT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
-              int refill_below) {
+              int refill_below, Phases ph) {
     constexpr int S = FastCfg<THREADS>::SS;
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_nodes = smem;
-    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem + (size_t)k_smem * 128);
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem + (size_t)k_smem * kSmemNodeStride);
     float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
     unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
-        reinterpret_cast<float4*>(s_nodes)[i] = __ldg(sc.wide_nodes + i);
+        reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
     if (lane == 0) {
         mbar_init(&s_bars[warp * 2], 1);
         mbar_init(&s_bars[warp * 2 + 1], 1);
@@ -593,8 +610,25 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             if (qn == 0 && feeder_exhausted(fd)) break;
             continue;
         }
-        if (shadow_round<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc) && has) {
+#pragma unroll 1
+        for (int it = 0; it < ph.node_iters; it++) {
+            shadow_node_step<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
+            const unsigned m = __ballot_sync(0xffffffffu, shadow_node_work(st, stk_base) && shadow_has_room<E, S>(st));
+            if (__popc(m) < ph.node_min) break;
+        }
+#pragma unroll 1
+        for (;;) {
+            shadow_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
+            const unsigned m = __ballot_sync(0xffffffffu, !st.occluded && st.tp != stk_ttop);
+            if (__popc(m) < ph.tri_min) break;
+        }
+        if (has && shadow_done<E, S>(st, stk_base)) {
+            // the next-event contribution waits in pend; an occluded ray cancels it
             if (st.occluded) __stcs(&pool.pend[slot], make_float4(0.f, 0.f, 0.f, 0.f));
+            st.np = stk_base;  // an occluded ray leaves entries behind
+            st.tp = stk_ttop;
+            st.nspill = 0;
+            st.occluded = false;
             has = false;
         }
     }
@@ -737,7 +771,7 @@ int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
 template <int THREADS>
 size_t fast_smem_bytes(int k_smem, bool shadow) {
     const size_t stack = shadow ? (size_t)FastCfg<THREADS>::SS * THREADS * 4 : (size_t)FastCfg<THREADS>::SC * THREADS * 8;
-    return (size_t)k_smem * 128 + stack +
+    return (size_t)k_smem * kSmemNodeStride + stack +
            (size_t)(THREADS / 32) * (kStageBytesPerWarp + 16 + (shadow ? kQueueBytesShadow : kQueueBytesClosest));
 }
 
@@ -746,14 +780,14 @@ void launch_extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims
                         const LaunchDims& dims, int* amb_out, cudaStream_t s) {
     const int k = min(dims.smem_nodes, sc.n_wide_nodes);
     k_extend_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, false), s>>>(
-        pool, sc, top, ctl, k, dims.refill_below, amb_out);
+        pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, amb_out);
 }
 template <int THREADS, bool COUNT>
 void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                         const LaunchDims& dims, cudaStream_t s) {
     const int k = min(dims.smem_nodes, sc.n_wide_nodes);
-    k_shadow_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, true), s>>>(pool, sc, top, ctl, k,
-                                                                                              dims.refill_below);
+    k_shadow_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, true), s>>>(
+        pool, sc, top, ctl, k, dims.refill_below, dims.shadow_phases);
 }
 
 template <bool COUNT>
@@ -812,7 +846,7 @@ size_t wf_fast_smem_bytes(int threads, int smem_nodes, bool shadow) {
 int wf_fast_max_smem_nodes(int threads, size_t smem_limit) {
     const size_t fixed = wf_fast_smem_bytes(threads, 0, false);  // the closest-hit kernel has the larger stacks
     if (fixed == 0 || fixed >= smem_limit) return 0;
-    return (int)((smem_limit - fixed) / 128);
+    return (int)((smem_limit - fixed) / kSmemNodeStride);
 }
 
 void wf_init_pool(const PoolView& pool, int* free_list, Control* ctl, cudaStream_t s) {

@@ -59,9 +59,17 @@ struct JobParams {
     int frame_stride;      // frame seed step between job-local frames
     int seed_base;         // 1984
     int n_frames;          // job-local frame count
-    const uint32_t* row_mats;  // h matrices, kXwMatWords words each: M^(w*row)
+    const uint4* row_a;        // h window tables of M^(w*row): words 0-3 of the 640 entries ...
+    const uint32_t* row_b;     // ... and word 4 (host/xorwow_tables.h xorwow_window_table)
     const XwColVec* col_vecs;  // n_frames * w entries: M^col * v0(frame)
     float* accum;              // caller's buffer, w*h records of 4 floats (x,y,z,pad)
+};
+
+// Phase lengths of the speculative while-while traversal (traverse_fast.cuh).
+struct Phases {
+    int node_iters;  // node steps per phase at most
+    int node_min;    // ... and only while at least this many lanes still have node work
+    int tri_min;     // extra triangle steps while at least this many lanes have a triangle waiting
 };
 
 struct LaunchDims {
@@ -69,6 +77,7 @@ struct LaunchDims {
     int fast_threads;   // threads of the persistent traversal CTAs (one CTA per SM): 512, 768 or 1024
     int smem_nodes;     // wide nodes staged into shared memory per CTA (top of the tree)
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
+    Phases closest_phases, shadow_phases;
 };
 
 // shared-memory bytes the persistent kernels need for a given configuration (0 = unsupported)

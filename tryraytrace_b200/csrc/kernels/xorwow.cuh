@@ -56,6 +56,31 @@ TRT_DEV void xw_matvec(const uint32_t* __restrict__ mat, const uint32_t in[5], u
     out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4;
 }
 
+// out = mat * in through the 4-bit window tables of host/xorwow_tables.h: 40 lookups.  The
+// table of one image row is shared by every sample of that row, so the 20-byte entries a warp
+// touches sit in a 12.8 KB L1-resident block; the 80 loads are independent of one another.
+constexpr int kXwWindowEntries = 40 * 16;
+TRT_DEV void xw_matvec_window(const uint4* __restrict__ ta, const uint32_t* __restrict__ tb, const uint32_t in[5],
+                              uint32_t out[5]) {
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+#pragma unroll
+    for (int w = 0; w < 5; w++) {
+        const uint32_t bits = in[w];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t e = (uint32_t)((w * 8 + k) * 16) + ((bits >> (4 * k)) & 15u);
+            const uint4 a = __ldg(ta + e);
+            const uint32_t b = __ldg(tb + e);
+            r0 ^= a.x;
+            r1 ^= a.y;
+            r2 ^= a.z;
+            r3 ^= a.w;
+            r4 ^= b;
+        }
+    }
+    out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4;
+}
+
 // seed scramble of curand_init (curand_kernel.h:800-812) for a seed that fits 32 bits
 TRT_DEV void xw_seed(uint32_t seed_lo, uint32_t v[5], uint32_t* d) {
     const uint32_t s0 = seed_lo ^ 0xaad26b49u;
