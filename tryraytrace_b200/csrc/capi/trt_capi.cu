@@ -537,6 +537,10 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
         tp.e2[i] = make_float4(t.e2[0], t.e2[1], t.e2[2], 0.f);
         tp.bmin[i] = make_float4(t.mn[0], t.mn[1], t.mn[2], 0.f);
         tp.bmax[i] = make_float4(t.mx[0], t.mx[1], t.mx[2], 0.f);
+        int ax = 0;
+        for (int k = 1; k < 3; k++)
+            if (t.mx[k] - t.mn[k] < t.mx[ax] - t.mn[ax]) ax = k;
+        tp.thin_axis[i] = ax;
     }
     tp.root_lo = make_float4(wb.root_mn[0], wb.root_mn[1], wb.root_mn[2], 0.f);
     tp.root_hi = make_float4(wb.root_mx[0], wb.root_mx[1], wb.root_mx[2], 0.f);

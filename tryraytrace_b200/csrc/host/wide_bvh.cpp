@@ -248,7 +248,14 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
         const Object& ob = objects[o];
         TopPrim tp;
         tp.v0[0] = ob.v0.x; tp.v0[1] = ob.v0.y; tp.v0[2] = ob.v0.z;
-        tp.id = o;
+        {   // like the tree's records: flag a primitive whose uploaded leaf box the vertex rule does not reproduce
+            float dmn[3], dmx[3];
+            derived_leaf_box(ob, dmn, dmx);
+            bool same = true;
+            for (int k = 0; k < 3; k++) same = same && dmn[k] == pbox[o].mn[k] && dmx[k] == pbox[o].mx[k];
+            tp.id = o | (same ? 0 : kTriNoDeriveBit);
+            if (!same) out.n_underivable++;
+        }
         tp.e1[0] = add_ftz(ob.v1.x, -ob.v0.x); tp.e1[1] = add_ftz(ob.v1.y, -ob.v0.y); tp.e1[2] = add_ftz(ob.v1.z, -ob.v0.z);
         tp.e2[0] = add_ftz(ob.v2.x, -ob.v0.x); tp.e2[1] = add_ftz(ob.v2.y, -ob.v0.y); tp.e2[2] = add_ftz(ob.v2.z, -ob.v0.z);
         for (int k = 0; k < 3; k++) { tp.mn[k] = pbox[o].mn[k]; tp.mx[k] = pbox[o].mx[k]; }

@@ -82,12 +82,13 @@ struct SceneDev {
 // it runs fully converged before a ray enters the tree.  root_lo/root_hi bound the tree.
 constexpr int kMaxTop = 12;
 struct TopPrims {
-    float4 v0[kMaxTop];    // v0.xyz, object id (int bits)
+    float4 v0[kMaxTop];    // v0.xyz, object id | kTriNoDerive (int bits)
     float4 e1[kMaxTop];    // v1 - v0 (single FTZ rounding, as reference :239), unused
     float4 e2[kMaxTop];    // v2 - v0
     float4 bmin[kMaxTop];  // reference leaf box as uploaded
     float4 bmax[kMaxTop];
     float4 root_lo, root_hi;
+    int thin_axis[kMaxTop];  // axis on which the leaf box is thinnest
     int n;
     int _pad[3];
 };

@@ -28,7 +28,10 @@
 //     passes with entry < t_w all of w's ancestors pass whenever the reference visits them, w is
 //     tested, and nothing tested beats it.  So candidates are accepted on the triangle test
 //     alone while traversing, and the leaf-box reach of the winner is checked once per ray; if
-//     it fails (FP corner cases, or a box that cannot be re-derived) the ray is replayed.
+//     it fails (FP corner cases, or a box that cannot be re-derived) the ray is replayed.  The
+//     check runs where the hit is CONSUMED (resolve_hit below: the shade kernel, or the unpack
+//     kernel of the parity entry points), one thread per ray at full lane occupancy, not inside
+//     the traversal loop where only the few lanes that just finished would take part.
 // Any-hit queries have a fixed interval, so (3) decides them exactly and no replay exists.
 //
 // Execution model (kernels in wavefront.cu).  One persistent CTA per SM.  Two levels:
@@ -260,12 +263,26 @@ struct NodeData {
 
 // `near_off` packs the byte offsets of the near-plane vectors inside the 128-byte node:
 // x: 0 or 16, y: 32 or 48, z: 64 or 80; the far plane is the other one of each pair (^16).
+// The first k_smem nodes are staged in shared memory 144 bytes apart (the 16-byte plane vector a
+// lane reads then falls into bank group (node + k) mod 8, so lanes reading the same k of
+// different nodes spread over the banks), the rest sit in global memory 128 bytes apart.  Both
+// are read through ONE generic-address code path: a warp whose lanes are split between the two
+// spaces issues the seven loads once, not twice.
+template <bool GENERIC>
 TRT_DEV void load_node(NodeData& n, const unsigned char* s_nodes, int k_smem, const float4* g_nodes, int node, int nxo,
                        int nyo, int nzo) {
-    if (node < k_smem) {
-        // staged nodes sit 144 bytes apart: the 16-byte plane vector a lane reads then falls into
-        // bank group (node + k) mod 8, so the lanes of a warp (all reading the same k of different
-        // nodes) spread over the banks instead of colliding on one group
+    const bool staged = node < k_smem;
+    if (GENERIC) {
+        const unsigned char* b = staged ? s_nodes + (size_t)node * kSmemNodeStride
+                                        : reinterpret_cast<const unsigned char*>(g_nodes) + (size_t)node * 128;
+        n.nx = *reinterpret_cast<const float4*>(b + nxo);
+        n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
+        n.ny = *reinterpret_cast<const float4*>(b + nyo);
+        n.fy = *reinterpret_cast<const float4*>(b + (nyo ^ 16));
+        n.nz = *reinterpret_cast<const float4*>(b + nzo);
+        n.fz = *reinterpret_cast<const float4*>(b + (nzo ^ 16));
+        n.ch = *reinterpret_cast<const int4*>(b + 96);
+    } else if (staged) {
         const unsigned char* b = s_nodes + node * kSmemNodeStride;
         n.nx = *reinterpret_cast<const float4*>(b + nxo);
         n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
@@ -298,13 +315,11 @@ struct ClosestRay {
     int nxo, nyo, nzo;  // near-plane byte offsets (see load_node)
     uint32_t np, tp;    // shared-window addresses of the next free node / triangle entry
     int nspill;         // entries in the local overflow
-    int win;            // where the current winner came from: >= 0 triangle record index in the tree,
-                        // -1 none, -2 - p root-level primitive p (its leaf box is verified at the end)
-};
+};  // `id` is the winner's object index | kTriNoDerive (as stored in its record), -1 = none
 
 // Tree-phase entry: the ray with the d_min / id / ambiguity the top phase found.
-TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, float d_min, int id, int win,
-                           uint32_t base, uint32_t ttop) {
+TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, float d_min, int id, uint32_t base,
+                           uint32_t ttop) {
     s.o = f3(o4.x, o4.y, o4.z);
     s.d = f3(d4.x, d4.y, d4.z);
     s.inv = f3(ref_safe_inv(s.d.x), ref_safe_inv(s.d.y), ref_safe_inv(s.d.z));
@@ -313,7 +328,6 @@ TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, floa
     s.nzo = s.inv.z < 0.f ? 80 : 64;
     s.d_min = d_min;
     s.id = id;
-    s.win = win;
     s.np = base;
     s.tp = ttop;
     s.nspill = 0;
@@ -325,8 +339,7 @@ TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, floa
 // runs this for its own ray.
 struct TopResult {
     float d_min;
-    int id;
-    int win;      // -1 none, -2 - p
+    int id;       // object index | kTriNoDerive, -1 none
     bool enters;  // the ray can reach something in the tree
 };
 TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
@@ -335,16 +348,14 @@ TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
     TopResult r;
     r.d_min = 1e20f;
     r.id = -1;
-    r.win = -1;
 #pragma unroll 1
     for (int p = 0; p < top.n; p++) {
         const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
         const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
         const int tid = f2i(a.w);
-        if (t > 0.f && (t < r.d_min || (t == r.d_min && tid < r.id))) {
+        if (t > 0.f && (t < r.d_min || (t == r.d_min && (tid & kTriIdMask) < (r.id & kTriIdMask)))) {
             r.d_min = t;
             r.id = tid;
-            r.win = -2 - p;
         }
     }
     float tn;
@@ -357,22 +368,30 @@ TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
 }
 
 // Deferred verification of a ray's winner (exactness argument, point 5): its reference leaf box
-// must pass the reference's slab test with an entry below the hit distance.
-TRT_DEV bool verify_winner(const SceneDev& sc, const TopPrims& top, const F3 o, const F3 d, int win, float t) {
-    if (win == -1) return true;  // a miss is a miss
-    float4 bmin, bmax;
-    if (win >= 0) {
-        const float4* tp = sc.tris + (size_t)win * 3;
-        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-        if (f2i(ta.w) & kTriNoDerive) return false;
-        derive_leaf_box(f3(ta.x, ta.y, ta.z), f3(tb.x, tb.y, tb.z), f3(tc.x, tc.y, tc.z), &bmin, &bmax);
-    } else {
-        bmin = top.bmin[-2 - win];
-        bmax = top.bmax[-2 - win];
+// must pass the reference's slab test with an entry below the hit distance; otherwise -- or when
+// the box cannot be re-derived from the vertices -- the ray is re-run in reference order.
+// `id` comes in as written by the traversal kernel (object index | kTriNoDerive, < 0 = miss) and
+// leaves as the final object index.  Returns true when the ray was replayed.
+TRT_DEV bool resolve_hit(const SceneDev& sc, const F3 o, const F3 d, float& t, int& id) {
+    if (id < 0) return false;  // a miss is a miss
+    bool ok = !(id & kTriNoDerive);
+    id &= kTriIdMask;
+    if (ok) {
+        const float4* op = sc.objects + (size_t)id * 7;
+        const float4 a = __ldg(op), b = __ldg(op + 1), c = __ldg(op + 2);
+        float4 bmin, bmax;
+        derive_leaf_box(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), &bmin, &bmax);
+        const F3 inv = f3(ref_safe_inv(d.x), ref_safe_inv(d.y), ref_safe_inv(d.z));
+        float entry;
+        ok = leaf_box_reach(bmin, bmax, o, inv, inv.x < 0.f, inv.y < 0.f, inv.z < 0.f, &entry) && entry < t;
     }
-    const F3 inv = f3(ref_safe_inv(d.x), ref_safe_inv(d.y), ref_safe_inv(d.z));
-    float entry;
-    return leaf_box_reach(bmin, bmax, o, inv, inv.x < 0.f, inv.y < 0.f, inv.z < 0.f, &entry) && entry < t;
+    if (ok) return false;
+    Ray r;
+    r.o = o;
+    r.d = d;
+    VisitCounts vc = {0, 0, 0};
+    id = ref_closest<false>(sc, r, &t, &vc);
+    return true;
 }
 
 // The traversal of one lane is cut into NODE steps and TRIANGLE steps; the kernels run them in
@@ -421,7 +440,7 @@ TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const S
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    load_node<true>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
     // slab intervals of the four children, packed two per instruction
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
@@ -468,11 +487,10 @@ TRT_DEV void closest_tri_step(const SceneDev& sc, ClosestRay& s, uint32_t base, 
     const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
     const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
     const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
-    const int tid = f2i(ta.w) & kTriIdMask;
-    if (t > 0.f && (t < s.d_min || (t == s.d_min && tid < s.id))) {
-        s.d_min = t;  // accepted on the triangle test alone; the winner is verified once per ray
+    const int tid = f2i(ta.w);
+    if (t > 0.f && (t < s.d_min || (t == s.d_min && (tid & kTriIdMask) < (s.id & kTriIdMask)))) {
+        s.d_min = t;  // accepted on the triangle test alone; the winner is verified where it is consumed
         s.id = tid;
-        s.win = tri;
     }
 }
 
@@ -510,20 +528,36 @@ TRT_DEV void shadow_begin(ShadowRay& s, const float4 o4, const float4 d4, uint32
 }
 
 // TOP PHASE, any hit: returns 1 = occluded by a root-level primitive, 2 = must traverse the tree,
-// 0 = unoccluded.  Same exact tests as the tree phase; the leaf-box test of a primitive is only
-// evaluated when some lane of the warp actually has a triangle hit inside its interval (walls
-// almost never shadow a ray that stays inside the room).  Called by all lanes of a warp.
-TRT_DEV int top_shadow(const TopPrims& top, const F3 o, const F3 d, float max_dist) {
+// 0 = unoccluded.  Called by all lanes of a warp.
+// A primitive occludes iff its triangle test hits inside the interval AND the reference can reach
+// it, i.e. its uploaded leaf box passes the reference's slab test (reference :295-303).  The slab
+// test is evaluated FIRST, and only partially: on the box's thinnest axis `a` the products
+// t1 = (lo_a - o_a) * inv_a, t2 = (hi_a - o_a) * inv_a are exactly the reference's, and when no
+// NaN can occur (all three reciprocals finite: a NaN needs 0 * inf) the reference's
+// tmax = min over axes of max(t1, t2) <= max(t1, t2) and tmin >= min(t1, t2), so
+// "max(t1,t2) > 0.001 and min(t1,t2) < max_dist" is NECESSARY for the box to pass.  A ray that
+// stays inside the room fails it for every wall (the flat wall boxes are 2e-3 thick), at a
+// fifth of the cost of the triangle test; the full tests run only for warps where some lane
+// passes it (or has a non-finite reciprocal).  Lanes whose slot holds no shadow ray (`live` false)
+// take no part in the decision.
+TRT_DEV int top_shadow(const TopPrims& top, const F3 o, const F3 d, float max_dist, bool live) {
     const F3 inv = f3(p_rcp(d.x), p_rcp(d.y), p_rcp(d.z));  // raw reciprocal, reference :276
     const float t_hi = p_sub(max_dist, 0.001f);
+    const float kInf = __int_as_float(0x7f800000);
+    const bool finite = fabsf(inv.x) < kInf && fabsf(inv.y) < kInf && fabsf(inv.z) < kInf;
     bool occluded = false;
 #pragma unroll 1
     for (int p = 0; p < top.n; p++) {
-        const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
-        const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
-        const bool hit = t > 0.001f && t < t_hi;
-        if (__any_sync(0xffffffffu, hit)) {
-            if (hit && ref_slab(top.bmin[p], top.bmax[p], o, inv, 0.001f, max_dist)) occluded = true;
+        const int ax = top.thin_axis[p];
+        const float4 lo4 = top.bmin[p], hi4 = top.bmax[p];
+        const float pl = ax == 0 ? lo4.x : (ax == 1 ? lo4.y : lo4.z), ph = ax == 0 ? hi4.x : (ax == 1 ? hi4.y : hi4.z);
+        const float oa = ax == 0 ? o.x : (ax == 1 ? o.y : o.z), ia = ax == 0 ? inv.x : (ax == 1 ? inv.y : inv.z);
+        const float t1 = p_mul(p_sub(pl, oa), ia), t2 = p_mul(p_sub(ph, oa), ia);
+        const bool maybe = live && (!finite || (fmaxf(t1, t2) > 0.001f && fminf(t1, t2) < max_dist));
+        if (__any_sync(0xffffffffu, maybe)) {
+            const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
+            const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
+            if (t > 0.001f && t < t_hi && ref_slab(lo4, hi4, o, inv, 0.001f, max_dist)) occluded = true;
         }
     }
     if (occluded) return 1;
@@ -563,7 +597,7 @@ TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const Sc
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    load_node<true>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
     const float4 az = plane_t(n.nz, s.o.z, s.inv.z), bz = plane_t(n.fz, s.o.z, s.inv.z);

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev s
 }
 
 // ---- shade: one thread per slot --------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict__ free_list, Control* ctl,
                                                   SceneDev sc, JobParams job) {
     __shared__ int scratch[2 + kBlock / 32];
@@ -211,11 +211,15 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
         }
         if (state == SLOT_ACTIVE) {
             const float2 hit = pool.hit[slot];
-            const int id = f2i(hit.y);
+            const float4 o4 = pool.ray_o[slot];
+            float t_hit = hit.x;
+            int id = f2i(hit.y);
+            // FAST traversal leaves the winner unverified (traverse_fast.cuh, point 5); REF ids pass through
+            if (FAST && resolve_hit(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), t_hit, id))
+                atomicAdd(&ctl->cnt_replays, 1ull);
             if (id < 0) {
                 terminated = true;  // miss: black environment (reference :427)
             } else {
-                const float4 o4 = pool.ray_o[slot];
                 const uint4 ra = pool.rng_a[slot];
                 const uint2 rb = pool.rng_b[slot];
                 io.ray.o = f3(o4.x, o4.y, o4.z);
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
                 io.prev_mode = (flags >> 16) & 0xff;
                 io.rng.v0 = ra.x; io.rng.v1 = ra.y; io.rng.v2 = ra.z; io.rng.v3 = ra.w;
                 io.rng.v4 = rb.x; io.rng.d = rb.y;
-                if (!shade_vertex(sc, job.rc, io, id, hit.x)) {
+                if (!shade_vertex(sc, job.rc, io, id, t_hit)) {
                     terminated = true;
                 } else {
                     const int depth = io.depth + 1;
@@ -382,7 +386,7 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
 template <int THREADS, bool COUNT>
 __global__ void __launch_bounds__(THREADS, 1)
 k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
-              int refill_below, Phases ph, int* amb_out) {
+              int refill_below, Phases ph) {
     constexpr int S = FastCfg<THREADS>::SC;
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -405,7 +409,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
     uint64_t* bars = s_bars + warp * 2;
     float4* q_o = reinterpret_cast<float4*>(s_queue + warp * kQueueBytesClosest);  // origin, d_min
-    float4* q_d = q_o + kQueueCap;                                                  // direction, winner so far (-1 / -2 - p)
+    float4* q_d = q_o + kQueueCap;                                                  // direction, winner so far (id | flag, -1 none)
     int* q_s = reinterpret_cast<int*>(q_d + kQueueCap);                             // pool slot
     constexpr uint32_t E = THREADS * 8;  // bytes between consecutive stack entries of one lane
     const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
@@ -422,7 +426,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     bool has = false;
     int slot = -1;
     int qn = 0;  // warp-uniform: entries in the tree-ray queue
-    unsigned replays = 0, rays = 0;
+    unsigned rays = 0;
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
         // 1. top phase on fresh chunks while the queue has room for a whole chunk
@@ -436,26 +440,14 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             const int my_slot = fd.cur_base + (int)lane;
             TopResult tr = top_closest(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
             if (live) rays++;
-            if (live && !tr.enters) {  // decided by the root-level list alone
-                const F3 ro = f3(o4.x, o4.y, o4.z), rd = f3(d4.x, d4.y, d4.z);
-                const bool ok = verify_winner(sc, top, ro, rd, tr.win, tr.d_min);
-                if (!ok) {  // rare: order-dependent reach, re-run in reference order
-                    Ray r;
-                    r.o = ro;
-                    r.d = rd;
-                    VisitCounts vc = {0, 0, 0};
-                    tr.id = ref_closest<false>(sc, r, &tr.d_min, &vc);
-                    replays++;
-                }
-                st_cs_f2(&pool.hit[my_slot], make_float2(tr.d_min, i2f(tr.id)));
-                if (amb_out) amb_out[my_slot] = ok ? 0 : 1;
-            }
+            // decided by the root-level list alone (the winner is verified by the consumer, resolve_hit)
+            if (live && !tr.enters) st_cs_f2(&pool.hit[my_slot], make_float2(tr.d_min, i2f(tr.id)));
             const bool tree = live && tr.enters;
             const unsigned m = __ballot_sync(0xffffffffu, tree);
             if (tree) {
                 const int qi = qn + __popc(m & lt_mask);
                 q_o[qi] = make_float4(o4.x, o4.y, o4.z, tr.d_min);
-                q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f(tr.win));
+                q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f(tr.id));
                 q_s[qi] = my_slot;
             }
             qn += __popc(m);
@@ -469,8 +461,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             if (!has && rank < qn) {
                 const int qi = qn - 1 - rank;
                 const float4 o4 = q_o[qi], d4 = q_d[qi];
-                const int win = f2i(d4.w);  // -1 or a root-level primitive
-                closest_begin(st, o4, d4, o4.w, win == -1 ? -1 : f2i(top.v0[-2 - win].w), win, stk_base, stk_ttop);
+                closest_begin(st, o4, d4, o4.w, f2i(d4.w), stk_base, stk_ttop);
                 slot = q_s[qi];
                 has = true;
             }
@@ -496,21 +487,9 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             const unsigned m = __ballot_sync(0xffffffffu, st.tp != stk_ttop);
             if (__popc(m) < ph.tri_min) break;
         }
-        // 5. finished rays write their hit
+        // 5. finished rays write their hit (verified by the consumer, resolve_hit)
         if (has && closest_done<E, S>(st, stk_base)) {
-            float t = st.d_min;
-            int id = st.id;
-            const bool ok = verify_winner(sc, top, st.o, st.d, st.win, t);
-            if (!ok) {  // rare: order-dependent reach, re-run in reference order
-                Ray r;
-                r.o = st.o;
-                r.d = st.d;
-                VisitCounts vc = {0, 0, 0};
-                id = ref_closest<false>(sc, r, &t, &vc);
-                replays++;
-            }
-            st_cs_f2(&pool.hit[slot], make_float2(t, i2f(id)));
-            if (amb_out) amb_out[slot] = ok ? 0 : 1;
+            st_cs_f2(&pool.hit[slot], make_float2(st.d_min, i2f(st.id)));
             has = false;
         }
     }
@@ -521,7 +500,6 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         warp_add(&ctl->cnt_nodes_closest, wc.nodes);
         warp_add(&ctl->cnt_tris_closest, wc.tris);
     }
-    warp_add(&ctl->cnt_replays, replays);
 }
 
 template <int THREADS, bool COUNT>
@@ -577,7 +555,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             const float4 o4 = buf[lane], d4 = buf[kChunk + lane];
             const bool live = f2i(d4.w) == 1;
             const int my_slot = fd.cur_base + (int)lane;
-            const int verdict = top_shadow(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), o4.w);
+            const int verdict = top_shadow(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), o4.w, live);
             if (live) rays++;
             // the next-event contribution waits in pend; an occluded ray cancels it
             if (live && verdict == 1) __stcs(&pool.pend[my_slot], make_float4(0.f, 0.f, 0.f, 0.f));
@@ -678,12 +656,20 @@ __global__ void __launch_bounds__(kBlock) k_pack_rays(PoolView pool, const float
     pool.pend[i] = make_float4(1.f, 1.f, 1.f, 0.f);
 }
 
-__global__ void __launch_bounds__(kBlock) k_unpack_hits(PoolView pool, int n, int* out_id, float* out_t) {
+// hits of the FAST kernel over a scratch pool -> caller's arrays, through the same winner
+// verification / replay the shade kernel applies; `out_replayed` marks the replayed rays
+__global__ void __launch_bounds__(kBlock) k_unpack_hits(PoolView pool, SceneDev sc, int n, int* out_id, float* out_t,
+                                                        int* out_replayed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float2 h = pool.hit[i];
-    if (out_id) out_id[i] = f2i(h.y);
-    if (out_t) out_t[i] = h.x;
+    const float4 o4 = pool.ray_o[i], d4 = pool.ray_d[i];
+    float t = h.x;
+    int id = f2i(h.y);
+    const bool replayed = resolve_hit(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), t, id);
+    if (out_id) out_id[i] = id;
+    if (out_t) out_t[i] = t;
+    if (out_replayed) out_replayed[i] = replayed ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(kBlock) k_unpack_occluded(PoolView pool, int n, int* out_occ) {
@@ -777,10 +763,10 @@ size_t fast_smem_bytes(int k_smem, bool shadow) {
 
 template <int THREADS, bool COUNT>
 void launch_extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
-                        const LaunchDims& dims, int* amb_out, cudaStream_t s) {
+                        const LaunchDims& dims, cudaStream_t s) {
     const int k = min(dims.smem_nodes, sc.n_wide_nodes);
     k_extend_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, false), s>>>(
-        pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, amb_out);
+        pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases);
 }
 template <int THREADS, bool COUNT>
 void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
@@ -792,11 +778,11 @@ void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims
 
 template <bool COUNT>
 void extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl, const LaunchDims& dims,
-                 int* amb_out, cudaStream_t s) {
+                 cudaStream_t s) {
     switch (dims.fast_threads) {
-    case 1024: launch_extend_fast<1024, COUNT>(pool, sc, top, ctl, dims, amb_out, s); break;
-    case 768: launch_extend_fast<768, COUNT>(pool, sc, top, ctl, dims, amb_out, s); break;
-    default: launch_extend_fast<512, COUNT>(pool, sc, top, ctl, dims, amb_out, s); break;
+    case 1024: launch_extend_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
+    case 768: launch_extend_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
+    default: launch_extend_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
 }
 template <bool COUNT>
@@ -879,10 +865,10 @@ static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, c
     k_prepare<<<1, 32, 0, s>>>(ctl);
     k_regen<<<persistent < full ? persistent : full, kBlock, 0, s>>>(pool, free_list, ctl, job);
     mark(1);
-    if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, nullptr, s);
+    if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(2);
-    k_shade<COUNT><<<full, kBlock, 0, s>>>(pool, free_list, ctl, sc, job);
+    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<full, kBlock, 0, s>>>(pool, free_list, ctl, sc, job);
     mark(3);
     if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
@@ -913,8 +899,8 @@ void wf_trace_primary(const SceneDev& sc, const JobParams& job, int, int travers
     // FAST: the production persistent kernel over a scratch pool; "entered" reports replayed rays
     k_pack_primary<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, job, d_ray);
     k_reset_cursors<<<1, 32, 0, s>>>(ctl);
-    extend_fast<false>(scratch, sc, top, ctl, dims, reinterpret_cast<int*>(d_entered), s);
-    k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_id, d_t);
+    extend_fast<false>(scratch, sc, top, ctl, dims, s);
+    k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, sc, n, d_id, d_t, reinterpret_cast<int*>(d_entered));
     (void)d_fetched;
     (void)d_tris;
 }
@@ -928,8 +914,8 @@ void wf_trace_closest(const SceneDev& sc, const float* d_rays, int n, int traver
     }
     k_pack_rays<<<grid_for(scratch.capacity), kBlock, 0, s>>>(scratch, d_rays, n);
     k_reset_cursors<<<1, 32, 0, s>>>(ctl);
-    extend_fast<false>(scratch, sc, top, ctl, dims, nullptr, s);
-    k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, n, d_id, d_t);
+    extend_fast<false>(scratch, sc, top, ctl, dims, s);
+    k_unpack_hits<<<grid_for(n), kBlock, 0, s>>>(scratch, sc, n, d_id, d_t, nullptr);
 }
 
 void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int traversal, int* d_occ,
