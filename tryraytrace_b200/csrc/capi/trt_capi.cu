@@ -212,8 +212,8 @@ int ensure_col_vecs(trt_ctx* c, size_t entries) {
 // One allocation, carved into the SoA arrays of PoolView (+ the free list when asked for).
 int alloc_pool(int cap, bool with_free_list, void** mem, PoolView* pool, int** free_list) {
     const size_t n = (size_t)cap;
-    // 8 float4/uint4 arrays + hit (float2) + rng_b (uint2) + free list (int)
-    const size_t bytes = n * (8 * 16 + 2 * 8 + (with_free_list ? 4 : 0));
+    // 7 float4/uint4 arrays + hit (float2) + rng_b (uint2) + free list (int)
+    const size_t bytes = n * (7 * 16 + 2 * 8 + (with_free_list ? 4 : 0));
     CU(cudaMalloc(mem, bytes));
     char* p = (char*)*mem;
     auto take = [&](size_t b) { void* r = p; p += b; return r; };
@@ -222,7 +222,6 @@ int alloc_pool(int cap, bool with_free_list, void** mem, PoolView* pool, int** f
     pool->thr = (float4*)take(n * 16);
     pool->rad = (float4*)take(n * 16);
     pool->pend = (float4*)take(n * 16);
-    pool->sh_o = (float4*)take(n * 16);
     pool->sh_d = (float4*)take(n * 16);
     pool->rng_a = (uint4*)take(n * 16);
     pool->hit = (float2*)take(n * 8);

@@ -9,6 +9,7 @@
 #include "traverse_fast.cuh"
 #include "traverse_ref.cuh"
 #include "trt_capi.h"
+#include <cstdlib>
 
 namespace trt {
 
@@ -186,32 +187,42 @@ __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev s
 }
 
 // ---- shade: one thread per slot --------------------------------------------------------
+// The kernel is a stream over ~250 bytes of path state per slot and is bound by how many of those
+// loads are in flight, so while the pool is mostly live (`eager`) every array of the slot is
+// requested up front, before the state word has come back; in the drain phase of a job, when
+// most slots are dead, the loads wait for the state check instead.
 template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict__ free_list, Control* ctl,
                                                   SceneDev sc, JobParams job) {
     __shared__ int scratch[2 + kBlock / 32];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of kBlock
+    const bool eager = ctl->alive * 2 > pool.capacity;
     const float4 d4 = pool.ray_d[slot];
+    float4 thr4, rad4, pend4, o4;
+    float2 hit;
+    uint4 ra;
+    uint2 rb;
+    if (eager) {
+        thr4 = pool.thr[slot]; rad4 = pool.rad[slot]; pend4 = pool.pend[slot]; o4 = pool.ray_o[slot];
+        hit = pool.hit[slot]; ra = pool.rng_a[slot]; rb = pool.rng_b[slot];
+    }
     const int flags = f2i(d4.w);
     const int state = flags & 0xff;
     bool terminated = false;
     if (state != SLOT_DEAD) {
+        if (!eager) {
+            thr4 = pool.thr[slot]; rad4 = pool.rad[slot]; pend4 = pool.pend[slot]; o4 = pool.ray_o[slot];
+            hit = pool.hit[slot]; ra = pool.rng_a[slot]; rb = pool.rng_b[slot];
+        }
         PathVertexIO io;
         io.shadow = false;
-        const float4 thr4 = pool.thr[slot];
-        const float4 rad4 = pool.rad[slot];
         const int pix = f2i(thr4.w);
         io.thr = f3(thr4.x, thr4.y, thr4.z);
         io.rad = f3(rad4.x, rad4.y, rad4.z);
         io.depth = (flags >> 8) & 0xff;
-        if (io.depth > 0) {
-            // next-event estimate of the previous vertex; the shadow kernel zeroed it if occluded
-            const float4 p = pool.pend[slot];
-            io.rad = v_add(io.rad, f3(p.x, p.y, p.z));
-        }
+        // next-event estimate of the previous vertex; the shadow kernel zeroed it if occluded
+        if (io.depth > 0) io.rad = v_add(io.rad, f3(pend4.x, pend4.y, pend4.z));
         if (state == SLOT_ACTIVE) {
-            const float2 hit = pool.hit[slot];
-            const float4 o4 = pool.ray_o[slot];
             float t_hit = hit.x;
             int id = f2i(hit.y);
             // FAST traversal leaves the winner unverified (traverse_fast.cuh, point 5); REF ids pass through
@@ -220,8 +231,6 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
             if (id < 0) {
                 terminated = true;  // miss: black environment (reference :427)
             } else {
-                const uint4 ra = pool.rng_a[slot];
-                const uint2 rb = pool.rng_b[slot];
                 io.ray.o = f3(o4.x, o4.y, o4.z);
                 io.ray.d = f3(d4.x, d4.y, d4.z);
                 io.prev_mode = (flags >> 16) & 0xff;
@@ -234,7 +243,9 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
                     // the reference loop ends after max_depth vertices; a path that still has a
                     // shadow ray in flight is finalised one iteration later (SLOT_FINISH)
                     const int ns = depth >= job.rc.max_depth ? SLOT_FINISH : SLOT_ACTIVE;
-                    pool.ray_o[slot] = make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, 0.f);
+                    // the shadow ray starts where the next ray starts (x_hit + nl * 1e-3, reference
+                    // :692 and :731): its length rides in ray_o.w, its direction in sh_d
+                    pool.ray_o[slot] = make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, io.shadow ? io.shadow_max_dist : 0.f);
                     pool.ray_d[slot] = make_float4(io.ray.d.x, io.ray.d.y, io.ray.d.z,
                                                    i2f(pack_flags(ns, depth, io.prev_mode)));
                     pool.thr[slot] = make_float4(io.thr.x, io.thr.y, io.thr.z, thr4.w);
@@ -243,8 +254,6 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
                     pool.rng_b[slot] = make_uint2(io.rng.v4, io.rng.d);
                     if (io.shadow) {
                         pool.pend[slot] = make_float4(io.shadow_contrib.x, io.shadow_contrib.y, io.shadow_contrib.z, 0.f);
-                        pool.sh_o[slot] = make_float4(io.shadow_ray.o.x, io.shadow_ray.o.y, io.shadow_ray.o.z,
-                                                      io.shadow_max_dist);
                         pool.sh_d[slot] = make_float4(io.shadow_ray.d.x, io.shadow_ray.d.y, io.shadow_ray.d.z, i2f(1));
                     } else {
                         pool.pend[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -278,7 +287,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_ref(PoolView pool, SceneDev s
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pool.capacity; slot += gridDim.x * blockDim.x) {
         const float4 d4 = pool.sh_d[slot];
         if (f2i(d4.w) != 1) continue;
-        const float4 o4 = pool.sh_o[slot];
+        const float4 o4 = pool.ray_o[slot];
         Ray r;
         r.o = f3(o4.x, o4.y, o4.z);
         r.d = f3(d4.x, d4.y, d4.z);
@@ -548,7 +557,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
         while (qn <= kQueueLow && !feeder_exhausted(fd)) {
-            feeder_advance(fd, stage, bars, pool.sh_o, pool.sh_d, &ctl->cursor_shadow, pool.capacity, lane,
+            feeder_advance(fd, stage, bars, pool.ray_o, pool.sh_d, &ctl->cursor_shadow, pool.capacity, lane,
                            act == 0 && qn == 0);
             if (!fd.fresh) break;
             const float4* buf = stage + fd.cur_buf * (2 * kChunk);
@@ -649,9 +658,8 @@ __global__ void __launch_bounds__(kBlock) k_pack_rays(PoolView pool, const float
         return;
     }
     const float* p = rays + (size_t)i * 8;
-    pool.ray_o[i] = make_float4(p[0], p[1], p[2], 0.f);
+    pool.ray_o[i] = make_float4(p[0], p[1], p[2], p[6]);
     pool.ray_d[i] = make_float4(p[3], p[4], p[5], i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
-    pool.sh_o[i] = make_float4(p[0], p[1], p[2], p[6]);
     pool.sh_d[i] = make_float4(p[3], p[4], p[5], i2f(1));
     pool.pend[i] = make_float4(1.f, 1.f, 1.f, 0.f);
 }
@@ -863,7 +871,10 @@ static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, c
     auto mark = [&](int i) { if (marks) cudaEventRecord(marks[i], s); };
     mark(0);
     k_prepare<<<1, 32, 0, s>>>(ctl);
-    k_regen<<<persistent < full ? persistent : full, kBlock, 0, s>>>(pool, free_list, ctl, job);
+    // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
+    // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up
+    const int regen_blocks = min(full, max(persistent, full / 4));
+    k_regen<<<regen_blocks, kBlock, 0, s>>>(pool, free_list, ctl, job);
     mark(1);
     if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);

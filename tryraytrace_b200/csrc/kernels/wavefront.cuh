@@ -19,16 +19,15 @@ namespace trt {
 
 enum { SLOT_DEAD = 0, SLOT_ACTIVE = 1, SLOT_FINISH = 2 };
 
-// Path slot, SoA: 144 bytes per slot over all arrays.
+// Path slot, SoA: 136 bytes per slot over all arrays.
 struct PoolView {
-    float4* ray_o;   // origin.xyz, unused
+    float4* ray_o;   // origin.xyz, length of the slot's shadow ray (it starts at the same point)
     float4* ray_d;   // direction.xyz, flags (int bits): state | depth << 8 | prev_mode << 16
     float2* hit;     // written by extend: t, hit object id (int bits, -1 = miss)
     float4* thr;     // throughput.xyz, pixel index (int bits)
     float4* rad;     // radiance.xyz, unused
     float4* pend;    // next-event contribution of the previous vertex (throughput applied), unused
-    float4* sh_o;    // shadow ray of this slot: origin.xyz, max_dist
-    float4* sh_d;    // direction.xyz, valid flag (int bits, 1 = trace it)
+    float4* sh_d;    // shadow ray of this slot: direction.xyz, valid flag (int bits, 1 = trace it)
     uint4* rng_a;    // XORWOW v0..v3
     uint2* rng_b;    // XORWOW v4, d
     int capacity;    // multiple of 256
