@@ -12,7 +12,7 @@ CXXFLAGS  := -O3 -march=x86-64-v3 -fopenmp -fPIC -std=c++17 $(INC) -Wall -Wno-un
 
 HOST_SRC  := loader bvh scene camera image_io pipeline renderer xorwow_tables wide_bvh
 HOST_OBJS := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(HOST_SRC)))
-CU_OBJS   := $(OBJDIR)/wavefront.o $(OBJDIR)/trt_capi.o
+CU_OBJS   := $(OBJDIR)/wavefront.o $(OBJDIR)/bvh_build.o $(OBJDIR)/trt_capi.o
 
 .PHONY: all lib oracle assets clean
 all: lib oracle assets
@@ -26,6 +26,10 @@ $(OBJDIR)/%.o: $(CSRC)/host/%.cpp $(wildcard include/*.h) $(wildcard $(CSRC)/hos
 $(OBJDIR)/wavefront.o: $(CSRC)/kernels/wavefront.cu $(wildcard $(CSRC)/kernels/*.cuh) include/trt_capi.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/wavefront.ptxas.log || (cat $(OBJDIR)/wavefront.ptxas.log; false)
+
+$(OBJDIR)/bvh_build.o: $(CSRC)/kernels/bvh_build.cu $(wildcard $(CSRC)/kernels/*.cuh)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(OBJDIR)/trt_capi.o: $(CSRC)/capi/trt_capi.cu $(wildcard $(CSRC)/kernels/*.cuh) $(wildcard $(CSRC)/host/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJDIR)

@@ -84,8 +84,16 @@ typedef struct {
     int n_wide_nodes, n_wide_leaf_tris, n_top_prims;
     int wide_node_bytes, tri_record_bytes;
     int wide_depth;
-    int reserved[6];
+    int builder;        /* TRT_BUILD_HOST_SAH or TRT_BUILD_DEVICE_LBVH: who built the wide BVH */
+    float build_ms;     /* wall time of the wide-BVH build (device builder: CUDA-event time) */
+    int n_underivable;  /* triangles whose uploaded leaf box the vertex rule does not reproduce */
+    int reserved[3];
 } trt_scene_info;
+
+/* Who re-lays-out the scene into the wide BVH the fast traversal reads (north-star subsystem 1:
+ * "bvh.cpp's output is re-laid out, or rebuilt on device").  AUTO = host SAH builder up to
+ * 256 Ki objects, device LBVH above. */
+enum { TRT_BUILD_AUTO = 0, TRT_BUILD_HOST_SAH = 1, TRT_BUILD_DEVICE_LBVH = 2 };
 
 const char* trt_last_error(void);
 const char* trt_version(void);
@@ -106,6 +114,16 @@ int trt_upload_scene(trt_ctx* ctx, const void* objects, int n_objects,
                      const void* nodes, int n_nodes,
                      const int* lights, int n_lights,
                      const trt_image* textures, int n_textures);
+/* Same, with an explicit builder.  With TRT_BUILD_DEVICE_LBVH `nodes` may be NULL (n_nodes 0):
+ * the scene is then built entirely on the device from the object array -- no BVH::build
+ * (reference src/bvh.cpp:32, 34 s for 10 M triangles) on the host at all.  Leaf boxes follow the
+ * reference builder's rule (src/bvh.cpp:12-30), hit ids are positions in `objects`, ties in t go
+ * to the lowest index; TRT_TRAVERSE_REF and the reference-order replay need the node array and are
+ * unavailable in that mode. */
+int trt_upload_scene_ex(trt_ctx* ctx, const void* objects, int n_objects,
+                        const void* nodes, int n_nodes,
+                        const int* lights, int n_lights,
+                        const trt_image* textures, int n_textures, int builder);
 int trt_scene_info_get(trt_ctx* ctx, trt_scene_info* out);
 
 /* Render = n_frames calls of launch_render_kernel (include/renderer.h:57,

@@ -10,7 +10,10 @@ import tryraytrace_b200 as trt
 config, spp, pool, mode = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
 warm = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 timed = int(sys.argv[6]) if len(sys.argv) > 6 else 0
-sc = trt.HostScene.from_config(config)
+import os, time
+t0 = time.time()
+sc = trt.HostScene.from_config(config, grid=int(os.environ.get('TRT_GRID', '0')))
+host_s = time.time() - t0
 cam, w, h = trt.config_camera(config)
 ctx = trt.Context(0)
 ctx.upload(sc)
@@ -29,4 +32,6 @@ line = f"ms/spp {ms / spp:.3f} Mrays/s {rays / ms / 1e3:.0f} rays/sample {rays /
 if timed:
     k = ctx.kernel_times()
     line += " | " + " ".join(f"{n[:-3]} {k[n]:.1f}" for n in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms"))
+inf = ctx.scene_info()
+line += f" | builder {inf['builder']} build_ms {inf['build_ms']:.1f} wide_nodes {inf['n_wide_nodes']} depth {inf['wide_depth']} host_prep_s {host_s:.1f}"
 print(line, "mean", float(acc.view(-1, 4)[:, :3].mean()) / (spp + warm))

@@ -39,6 +39,9 @@ CAMERA = np.dtype([("pos", VEC), ("cx", VEC), ("cy", VEC), ("dir", VEC),
 assert OBJECT.itemsize == 112 and NODE.itemsize == 48 and CAMERA.itemsize == 80 and VEC.itemsize == 16
 
 
+BUILD_AUTO, BUILD_HOST_SAH, BUILD_DEVICE_LBVH = 0, 1, 2
+
+
 class TrtError(RuntimeError):
     pass
 
@@ -69,10 +72,12 @@ class KernelTimes(C.Structure):
 class SceneInfo(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n_objects", "n_ref_nodes", "n_lights", "n_textures", "n_wide_nodes",
                                        "n_wide_leaf_tris", "n_top_prims", "wide_node_bytes", "tri_record_bytes",
-                                       "wide_depth")] + [("reserved", C.c_int * 6)]
+                                       "wide_depth", "builder")] + [("build_ms", C.c_float), ("n_underivable", C.c_int),
+                                                                    ("reserved", C.c_int * 3)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: (float(getattr(self, n)) if n == "build_ms" else int(getattr(self, n)))
+                for n, _ in self._fields_ if n != "reserved"}
 
 
 class Image(C.Structure):
@@ -284,9 +289,11 @@ class Context:
             pass
 
     # init_scene_data (reference include/renderer.h:35-38)
-    def init_scene_data(self, objects, texture_files, nodes, light_indices):
+    def init_scene_data(self, objects, texture_files, nodes, light_indices, builder=0):
+        """builder: BUILD_AUTO / BUILD_HOST_SAH / BUILD_DEVICE_LBVH (include/trt_capi.h).  nodes=None with the
+        device builder builds the scene from the object array alone (no BVH::build on the host)."""
         objs = np.ascontiguousarray(objects, dtype=OBJECT)
-        nd = np.ascontiguousarray(nodes, dtype=NODE)
+        nd = np.ascontiguousarray(nodes, dtype=NODE) if nodes is not None else np.zeros(0, dtype=NODE)
         li = np.ascontiguousarray(light_indices, dtype=np.int32)
         imgs, keep = [], []
         for f in texture_files:
@@ -294,11 +301,11 @@ class Context:
             keep.append(a)
             imgs.append(Image(a.shape[1], a.shape[0], a.ctypes.data))
         arr = (Image * max(len(imgs), 1))(*imgs)
-        _check(lib().trt_upload_scene(self._h, _np_ptr(objs), len(objs), _np_ptr(nd), len(nd),
-                                      _np_ptr(li) if len(li) else None, len(li), arr, len(imgs)))
+        _check(lib().trt_upload_scene_ex(self._h, _np_ptr(objs), len(objs), _np_ptr(nd) if len(nd) else None, len(nd),
+                                         _np_ptr(li) if len(li) else None, len(li), arr, len(imgs), int(builder)))
 
-    def upload(self, scene: HostScene):
-        self.init_scene_data(scene.objects, scene.texture_files, scene.nodes, scene.lights)
+    def upload(self, scene: HostScene, builder=0):
+        self.init_scene_data(scene.objects, scene.texture_files, scene.nodes, scene.lights, builder)
 
     def scene_info(self):
         s = SceneInfo()

@@ -10,9 +10,11 @@
 
 #include "../host/wide_bvh.h"
 #include "../host/xorwow_tables.h"
+#include "../kernels/bvh_build.cuh"
 #include "../kernels/wavefront.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -46,7 +48,8 @@ int fail(int code, const char* fmt, ...) {
 constexpr int kFrameChunk = 64;       // frames per wavefront job (bounds the column-vector table)
 constexpr int kBatchIterations = 16;  // iterations issued between completion polls
 constexpr int kDefaultPool = 1 << 20;
-constexpr int kWideStackEntries = 48;  // kernels/traverse_wide.cuh kNodeStack
+constexpr int kWideStackEntries = 128;  // kernels/traverse_fast.cuh kSpillEntries
+constexpr int kAutoDeviceBuildAbove = 1 << 18;  // TRT_BUILD_AUTO: objects above which the device builder is used
 
 }  // namespace
 
@@ -321,6 +324,8 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if ((long long)w * h > (1ll << 30)) return fail(TRT_ERR_ARG, "image too large");
     trt_opts o;
     if (int rc = check_opts(opts_in, &o)) return rc;
+    if (o.traversal == TRT_TRAVERSE_REF && c->sc.n_ref_nodes == 0)
+        return fail(TRT_ERR_STATE, "TRT_TRAVERSE_REF needs the reference node array (scene was built on the device without it)");
     if ((long long)o.seed_base + first < 0) return fail(TRT_ERR_ARG, "negative RNG seed");
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_rng_tables(c, w, h)) return rc;
@@ -459,13 +464,24 @@ int trt_destroy(trt_ctx* c) {
     return 0;
 }
 
-int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void* nodes, int n_nodes,
-                     const int* lights, int n_lights, const trt_image* textures, int n_textures) {
+int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const void* nodes, int n_nodes,
+                        const int* lights, int n_lights, const trt_image* textures, int n_textures, int builder) {
     if (!c) return fail(TRT_ERR_ARG, "null context");
     if (!objects || n_objects <= 0) return fail(TRT_ERR_ARG, "empty object array");
-    if (!nodes || n_nodes <= 0) return fail(TRT_ERR_ARG, "empty node array");
+    if (builder != TRT_BUILD_AUTO && builder != TRT_BUILD_HOST_SAH && builder != TRT_BUILD_DEVICE_LBVH)
+        return fail(TRT_ERR_ARG, "unknown builder %d", builder);
+    if (const char* e = getenv("TRT_BUILDER")) {  // tuning override: 1 = host SAH, 2 = device LBVH
+        const int v = atoi(e);
+        if (v == TRT_BUILD_HOST_SAH || v == TRT_BUILD_DEVICE_LBVH) builder = v;
+    }
+    if (builder == TRT_BUILD_AUTO)
+        builder = (!nodes || n_objects > kAutoDeviceBuildAbove) ? TRT_BUILD_DEVICE_LBVH : TRT_BUILD_HOST_SAH;
+    const bool have_ref = nodes && n_nodes > 0;
+    if (!have_ref && builder != TRT_BUILD_DEVICE_LBVH)
+        return fail(TRT_ERR_ARG, "empty node array (only TRT_BUILD_DEVICE_LBVH can build without the reference nodes)");
     if (n_lights < 0 || (n_lights > 0 && !lights)) return fail(TRT_ERR_ARG, "bad light list");
     if (n_textures < 0 || n_textures > 5) return fail(TRT_ERR_ARG, "at most 5 textures (MAX_TEXTURES)");
+    if (n_objects >= (1 << 29)) return fail(TRT_ERR_ARG, "too many objects");
     const Object* objs = (const Object*)objects;
     const LinearBVHNode* nd = (const LinearBVHNode*)nodes;
     // validate what the kernels will index with
@@ -473,7 +489,7 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
         if (lights[i] < 0 || lights[i] >= n_objects) return fail(TRT_ERR_ARG, "light index %d out of range", lights[i]);
     for (int i = 0; i < n_objects; i++)
         if (objs[i].tex_id >= n_textures) return fail(TRT_ERR_ARG, "object %d uses texture %d, only %d given", i, objs[i].tex_id, n_textures);
-    for (int i = 0; i < n_nodes; i++) {
+    for (int i = 0; have_ref && i < n_nodes; i++) {
         const LinearBVHNode& n = nd[i];
         if (n.is_leaf) {
             if (n.primitive_offset < 0 || n.primitive_count < 0 || n.primitive_offset + n.primitive_count > n_objects)
@@ -489,8 +505,10 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
 
     CU(cudaMalloc(&c->d_objects, (size_t)n_objects * sizeof(Object)));
     CU(cudaMemcpy(c->d_objects, objs, (size_t)n_objects * sizeof(Object), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&c->d_ref_nodes, (size_t)n_nodes * sizeof(LinearBVHNode)));
-    CU(cudaMemcpy(c->d_ref_nodes, nd, (size_t)n_nodes * sizeof(LinearBVHNode), cudaMemcpyHostToDevice));
+    if (have_ref) {
+        CU(cudaMalloc(&c->d_ref_nodes, (size_t)n_nodes * sizeof(LinearBVHNode)));
+        CU(cudaMemcpy(c->d_ref_nodes, nd, (size_t)n_nodes * sizeof(LinearBVHNode), cudaMemcpyHostToDevice));
+    }
     if (n_lights) {
         CU(cudaMalloc(&c->d_lights, (size_t)n_lights * sizeof(int)));
         CU(cudaMemcpy(c->d_lights, lights, (size_t)n_lights * sizeof(int), cudaMemcpyHostToDevice));
@@ -502,14 +520,58 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
     }
 
     // re-layout for the fast path: wide BVH over the reference leaf boxes + triangle records
-    WideBvh wb;
-    build_wide_bvh(objs, n_objects, nd, n_nodes, wb);
-    if (3 * wb.depth + 1 > kWideStackEntries)
-        return fail(TRT_ERR_ARG, "wide BVH depth %d exceeds the traversal stack", wb.depth);
-    CU(cudaMalloc(&c->d_wide_nodes, std::max<size_t>(wb.nodes.size(), 1) * sizeof(WideNode)));
-    CU(cudaMemcpy(c->d_wide_nodes, wb.nodes.data(), wb.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&c->d_tris, std::max<size_t>(wb.tris.size(), 1) * sizeof(TriRecord)));
-    CU(cudaMemcpy(c->d_tris, wb.tris.data(), wb.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
+    TopPrims& tp = c->top;
+    memset(&tp, 0, sizeof(tp));
+    int n_wide = 0, n_tris = 0, n_top = 0, depth = 0, n_underivable = 0;
+    float build_ms = 0.f;
+    if (builder == TRT_BUILD_DEVICE_LBVH) {
+        int max_leaf = 4;
+        if (const char* e = getenv("TRT_MAX_LEAF")) max_leaf = std::max(1, std::min(4, atoi(e)));
+        DeviceWideBvh dw;
+        std::string err;
+        if (build_wide_bvh_device(c->d_objects, n_objects, c->d_ref_nodes, have_ref ? n_nodes : 0, max_leaf, &dw, c->stream,
+                                  &err) != 0) {
+            cudaFree(dw.d_nodes);
+            cudaFree(dw.d_tris);
+            cudaGetLastError();
+            return fail(TRT_ERR_CUDA, "device BVH build: %s", err.c_str());
+        }
+        c->d_wide_nodes = dw.d_nodes;
+        c->d_tris = dw.d_tris;
+        tp = dw.top;
+        n_wide = dw.n_nodes; n_tris = dw.n_tris; n_top = dw.n_top; depth = dw.depth; n_underivable = dw.n_underivable;
+        build_ms = dw.build_ms;
+    } else {
+        const auto t0 = std::chrono::steady_clock::now();
+        WideBvh wb;
+        build_wide_bvh(objs, n_objects, nd, n_nodes, wb);
+        build_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        CU(cudaMalloc(&c->d_wide_nodes, std::max<size_t>(wb.nodes.size(), 1) * sizeof(WideNode)));
+        CU(cudaMemcpy(c->d_wide_nodes, wb.nodes.data(), wb.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&c->d_tris, std::max<size_t>(wb.tris.size(), 1) * sizeof(TriRecord)));
+        CU(cudaMemcpy(c->d_tris, wb.tris.data(), wb.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
+        tp.n = (int)wb.top.size();
+        for (int i = 0; i < tp.n; i++) {
+            const TopPrim& t = wb.top[i];
+            tp.v0[i] = make_float4(t.v0[0], t.v0[1], t.v0[2], __int_as_float_host(t.id));
+            tp.e1[i] = make_float4(t.e1[0], t.e1[1], t.e1[2], 0.f);
+            tp.e2[i] = make_float4(t.e2[0], t.e2[1], t.e2[2], 0.f);
+            tp.bmin[i] = make_float4(t.mn[0], t.mn[1], t.mn[2], 0.f);
+            tp.bmax[i] = make_float4(t.mx[0], t.mx[1], t.mx[2], 0.f);
+            int ax = 0;
+            for (int k = 1; k < 3; k++)
+                if (t.mx[k] - t.mn[k] < t.mx[ax] - t.mn[ax]) ax = k;
+            tp.thin_axis[i] = ax;
+        }
+        tp.root_lo = make_float4(wb.root_mn[0], wb.root_mn[1], wb.root_mn[2], 0.f);
+        tp.root_hi = make_float4(wb.root_mx[0], wb.root_mx[1], wb.root_mx[2], 0.f);
+        n_wide = (int)wb.nodes.size(); n_tris = (int)wb.tris.size(); n_top = wb.n_top_prims; depth = wb.depth;
+        n_underivable = wb.n_underivable;
+    }
+    if (3 * depth + 1 > kWideStackEntries) {
+        free_scene(c);
+        return fail(TRT_ERR_ARG, "wide BVH depth %d exceeds the traversal stack", depth);
+    }
 
     SceneDev& sc = c->sc;
     memset(&sc, 0, sizeof(sc));
@@ -517,47 +579,39 @@ int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void*
     sc.ref_nodes = c->d_ref_nodes;
     sc.lights = c->d_lights;
     sc.n_objects = n_objects;
-    sc.n_ref_nodes = n_nodes;
+    sc.n_ref_nodes = have_ref ? n_nodes : 0;
     sc.n_lights = n_lights;
     sc.n_textures = n_textures;
     for (int i = 0; i < n_textures; i++) sc.tex[i] = c->tex_objs[i];
     sc.wide_nodes = c->d_wide_nodes;
     sc.tris = c->d_tris;
-    sc.n_wide_nodes = (int)wb.nodes.size();
-    sc.n_tris = (int)wb.tris.size();
-
-    TopPrims& tp = c->top;
-    memset(&tp, 0, sizeof(tp));
-    tp.n = (int)wb.top.size();
-    for (int i = 0; i < tp.n; i++) {
-        const TopPrim& t = wb.top[i];
-        tp.v0[i] = make_float4(t.v0[0], t.v0[1], t.v0[2], __int_as_float_host(t.id));
-        tp.e1[i] = make_float4(t.e1[0], t.e1[1], t.e1[2], 0.f);
-        tp.e2[i] = make_float4(t.e2[0], t.e2[1], t.e2[2], 0.f);
-        tp.bmin[i] = make_float4(t.mn[0], t.mn[1], t.mn[2], 0.f);
-        tp.bmax[i] = make_float4(t.mx[0], t.mx[1], t.mx[2], 0.f);
-        int ax = 0;
-        for (int k = 1; k < 3; k++)
-            if (t.mx[k] - t.mn[k] < t.mx[ax] - t.mn[ax]) ax = k;
-        tp.thin_axis[i] = ax;
-    }
-    tp.root_lo = make_float4(wb.root_mn[0], wb.root_mn[1], wb.root_mn[2], 0.f);
-    tp.root_hi = make_float4(wb.root_mx[0], wb.root_mx[1], wb.root_mx[2], 0.f);
+    sc.n_wide_nodes = n_wide;
+    sc.n_tris = n_tris;
 
     trt_scene_info& in = c->info;
     memset(&in, 0, sizeof(in));
     in.n_objects = n_objects;
-    in.n_ref_nodes = n_nodes;
+    in.n_ref_nodes = sc.n_ref_nodes;
     in.n_lights = n_lights;
     in.n_textures = n_textures;
-    in.n_wide_nodes = (int)wb.nodes.size();
-    in.n_wide_leaf_tris = (int)wb.tris.size();
-    in.n_top_prims = wb.n_top_prims;
+    in.n_wide_nodes = n_wide;
+    in.n_wide_leaf_tris = n_tris;
+    in.n_top_prims = n_top;
     in.wide_node_bytes = (int)sizeof(WideNode);
     in.tri_record_bytes = (int)sizeof(TriRecord);
-    in.wide_depth = wb.depth;
+    in.wide_depth = depth;
+    in.builder = builder;
+    in.build_ms = build_ms;
+    in.n_underivable = n_underivable;
     c->have_scene = true;
     return 0;
+}
+
+int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void* nodes, int n_nodes,
+                     const int* lights, int n_lights, const trt_image* textures, int n_textures) {
+    if (!nodes || n_nodes <= 0) return fail(TRT_ERR_ARG, "empty node array");
+    return trt_upload_scene_ex(c, objects, n_objects, nodes, n_nodes, lights, n_lights, textures, n_textures,
+                               TRT_BUILD_AUTO);
 }
 
 int trt_scene_info_get(trt_ctx* c, trt_scene_info* out) {
@@ -599,6 +653,7 @@ int trt_trace_primary(trt_ctx* c, int w, int h, int frame_seed, const void* cam,
     if (!c->have_scene) return fail(TRT_ERR_STATE, "trt_trace_primary before trt_upload_scene");
     if (w <= 0 || h <= 0) return fail(TRT_ERR_ARG, "bad dimensions");
     if (traversal != TRT_TRAVERSE_FAST && traversal != TRT_TRAVERSE_REF) return fail(TRT_ERR_ARG, "unknown traversal mode");
+    if (traversal == TRT_TRAVERSE_REF && c->sc.n_ref_nodes == 0) return fail(TRT_ERR_STATE, "TRT_TRAVERSE_REF needs the reference node array");
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_rng_tables(c, w, h)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)w)) return rc;
@@ -621,6 +676,7 @@ int trt_trace_closest(trt_ctx* c, const float* d_rays, int n, int traversal, int
     if (!c || !d_rays || !d_id) return fail(TRT_ERR_ARG, "null pointer");
     if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
     if (n <= 0) return 0;
+    if (traversal == TRT_TRAVERSE_REF && c->sc.n_ref_nodes == 0) return fail(TRT_ERR_STATE, "TRT_TRAVERSE_REF needs the reference node array");
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_scratch(c, n)) return rc;
     wf_trace_closest(c->sc, d_rays, n, traversal, d_id, d_t, c->top, c->scratch, c->d_ctl, launch_dims(c), c->stream);
@@ -634,6 +690,7 @@ int trt_trace_shadow(trt_ctx* c, const float* d_rays, int n, int traversal, int*
     if (!c || !d_rays || !d_occ) return fail(TRT_ERR_ARG, "null pointer");
     if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
     if (n <= 0) return 0;
+    if (traversal == TRT_TRAVERSE_REF && c->sc.n_ref_nodes == 0) return fail(TRT_ERR_STATE, "TRT_TRAVERSE_REF needs the reference node array");
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_scratch(c, n)) return rc;
     wf_trace_shadow(c->sc, d_rays, n, traversal, d_occ, c->top, c->scratch, c->d_ctl, launch_dims(c), c->stream);

@@ -1,0 +1,651 @@
+// bvh_build.cu -- see bvh_build.cuh.  LBVH over 63-bit Morton codes of the reference leaf-box
+// centroids (Karras 2012: one thread per internal node finds its key range and split with
+// count-leading-zeros searches; boxes are fitted bottom-up with one atomic counter per node),
+// then a breadth-first collapse into 4-wide nodes (open the inner child with the largest box,
+// like the host builder) with device-side allocation of the output nodes.
+#include "bvh_build.cuh"
+#include "traverse_fast.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace trt {
+namespace {
+
+constexpr int kB = 256;
+constexpr int kFlagValid = 1, kFlagTop = 2;  // kTriNoDerive (bit 30) rides in the same word
+constexpr int kCandCap = 1024;
+
+struct Bounds {
+    float mn[3], mx[3];
+    int count, aux;
+};
+
+struct Task {
+    int bnode, wide, depth;
+};
+
+__device__ __forceinline__ void atomic_min_f(float* a, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float* a, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+}
+
+__global__ void k_init_bounds(Bounds* b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float inf = __int_as_float(0x7f800000);
+    for (int k = 0; k < 3; k++) { b[i].mn[k] = inf; b[i].mx[k] = -inf; }
+    b[i].count = b[i].aux = 0;
+}
+
+__global__ void k_init_boxes(float4* lo, float4* hi, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float inf = __int_as_float(0x7f800000);
+    lo[i] = make_float4(inf, inf, inf, 0.f);
+    hi[i] = make_float4(-inf, -inf, -inf, 0.f);
+}
+
+// reference leaf box of every object = union of the leaf nodes that refer to it
+__global__ void k_boxes_from_ref(const float4* __restrict__ ref_nodes, int n_nodes, float4* lo, float4* hi,
+                                 int n_objects) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int4 link = __ldg(reinterpret_cast<const int4*>(ref_nodes + (size_t)i * 3 + 2));
+    if (!link.w) return;
+    const float4 bmin = __ldg(ref_nodes + (size_t)i * 3), bmax = __ldg(ref_nodes + (size_t)i * 3 + 1);
+    for (int k = 0; k < link.y; k++) {
+        const int o = link.x + k;
+        if (o < 0 || o >= n_objects) continue;
+        atomic_min_f(&lo[o].x, bmin.x); atomic_min_f(&lo[o].y, bmin.y); atomic_min_f(&lo[o].z, bmin.z);
+        atomic_max_f(&hi[o].x, bmax.x); atomic_max_f(&hi[o].y, bmax.y); atomic_max_f(&hi[o].z, bmax.z);
+    }
+}
+
+__global__ void k_boxes_derived(const float4* __restrict__ objects, int n, float4* lo, float4* hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* op = objects + (size_t)i * 7;
+    const float4 a = __ldg(op), b = __ldg(op + 1), c = __ldg(op + 2);
+    float4 bmin, bmax;
+    derive_leaf_box(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), &bmin, &bmax);
+    lo[i] = bmin;
+    hi[i] = bmax;
+}
+
+// block-wide min/max of a box + count, one set of atomics per block
+__device__ void reduce_bounds(bool take, float3 mn, float3 mx, Bounds* out) {
+    __shared__ float s_mn[3][kB / 32], s_mx[3][kB / 32];
+    __shared__ int s_cnt[kB / 32];
+    const float inf = __int_as_float(0x7f800000);
+    float v[6] = {take ? mn.x : inf, take ? mn.y : inf, take ? mn.z : inf, take ? mx.x : -inf, take ? mx.y : -inf,
+                  take ? mx.z : -inf};
+    int cnt = take ? 1 : 0;
+    for (int off = 16; off; off >>= 1) {
+        for (int k = 0; k < 3; k++) {
+            v[k] = fminf(v[k], __shfl_xor_sync(0xffffffffu, v[k], off));
+            v[3 + k] = fmaxf(v[3 + k], __shfl_xor_sync(0xffffffffu, v[3 + k], off));
+        }
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        for (int k = 0; k < 3; k++) { s_mn[k][warp] = v[k]; s_mx[k][warp] = v[3 + k]; }
+        s_cnt[warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        float m[6] = {inf, inf, inf, -inf, -inf, -inf};
+        for (int w = 0; w < kB / 32; w++) {
+            for (int k = 0; k < 3; k++) { m[k] = fminf(m[k], s_mn[k][w]); m[3 + k] = fmaxf(m[3 + k], s_mx[k][w]); }
+            total += s_cnt[w];
+        }
+        if (total) {
+            for (int k = 0; k < 3; k++) { atomic_min_f(&out->mn[k], m[k]); atomic_max_f(&out->mx[k], m[3 + k]); }
+            atomicAdd(&out->count, total);
+        }
+    }
+}
+
+// validity + "the vertex rule reproduces the uploaded leaf box" flag per object, scene bounds
+__global__ void __launch_bounds__(kB) k_flags(const float4* __restrict__ objects, int n, const float4* __restrict__ lo,
+                                              const float4* __restrict__ hi, int* flags, Bounds* scene) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    float4 l = make_float4(0, 0, 0, 0), h = l;
+    if (i < n) {
+        l = lo[i];
+        h = hi[i];
+        valid = h.x >= l.x && h.y >= l.y && h.z >= l.z;
+        int f = 0;
+        if (valid) {
+            const float4* op = objects + (size_t)i * 7;
+            const float4 a = __ldg(op), b = __ldg(op + 1), c = __ldg(op + 2);
+            float4 bmin, bmax;
+            derive_leaf_box(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), &bmin, &bmax);
+            const bool same = bmin.x == l.x && bmin.y == l.y && bmin.z == l.z && bmax.x == h.x && bmax.y == h.y && bmax.z == h.z;
+            f = kFlagValid | (same ? 0 : kTriNoDerive);
+            if (!same) atomicAdd(&scene->aux, 1);
+        }
+        flags[i] = f;
+    }
+    reduce_bounds(valid, make_float3(l.x, l.y, l.z), make_float3(h.x, h.y, h.z), scene);
+}
+
+__device__ __forceinline__ float box_area(float4 l, float4 h) {
+    const float dx = h.x - l.x, dy = h.y - l.y, dz = h.z - l.z;
+    if (dx < 0.f || dy < 0.f || dz < 0.f) return 0.f;
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+}
+
+__global__ void k_select_top(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ flags,
+                             int n, float thr_area, int2* cand, int* n_cand) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !(flags[i] & kFlagValid)) return;
+    const float a = box_area(lo[i], hi[i]);
+    if (a >= thr_area) {
+        const int k = atomicAdd(n_cand, 1);
+        if (k < kCandCap) cand[k] = make_int2(i, __float_as_int(a));
+    }
+}
+
+__global__ void k_mark_top(int* flags, const int* ids, int n_top) {
+    const int i = threadIdx.x;
+    if (i < n_top) flags[ids[i]] |= kFlagTop;
+}
+
+__global__ void __launch_bounds__(kB) k_centroid_bounds(const float4* __restrict__ lo, const float4* __restrict__ hi,
+                                                        const int* __restrict__ flags, int n, Bounds* cb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    float3 c = make_float3(0, 0, 0);
+    if (i < n) {
+        const int f = flags[i];
+        take = (f & kFlagValid) && !(f & kFlagTop);
+        const float4 l = lo[i], h = hi[i];
+        c = make_float3(0.5f * (l.x + h.x), 0.5f * (l.y + h.y), 0.5f * (l.z + h.z));
+    }
+    reduce_bounds(take, c, c, cb);
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long x) {  // 21 bits -> every third bit
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ flags,
+                         int n, float3 cmin, float3 scale, unsigned long long* keys, int* idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    idx[i] = i;
+    const int f = flags[i];
+    if (!(f & kFlagValid) || (f & kFlagTop)) {
+        keys[i] = ~0ull;  // sorts behind every real key
+        return;
+    }
+    const float4 l = lo[i], h = hi[i];
+    const float q[3] = {(0.5f * (l.x + h.x) - cmin.x) * scale.x, (0.5f * (l.y + h.y) - cmin.y) * scale.y,
+                        (0.5f * (l.z + h.z) - cmin.z) * scale.z};
+    unsigned long long k = 0;
+    for (int a = 0; a < 3; a++) {
+        const float v = fminf(fmaxf(q[a], 0.f), 2097151.f);
+        k |= spread21((unsigned long long)v) << (2 - a);
+    }
+    keys[i] = k;  // 63 bits: strictly below ~0ull
+}
+
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+// Karras 2012, one thread per internal node.  Children: >= 0 internal node, < 0 leaf ~index
+// (index into the sorted order).
+__global__ void k_hierarchy(const unsigned long long* __restrict__ keys, int n, int* left, int* right, int* parent_int,
+                            int* parent_leaf, int* first, int* last) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) / 2;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int a = min(i, j), b = max(i, j);
+    const int lc = a == gamma ? ~gamma : gamma;
+    const int rc = b == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+    left[i] = lc;
+    right[i] = rc;
+    first[i] = a;
+    last[i] = b;
+    if (lc < 0) parent_leaf[~lc] = i; else parent_int[lc] = i;
+    if (rc < 0) parent_leaf[~rc] = i; else parent_int[rc] = i;
+    if (i == 0) parent_int[0] = -1;
+}
+
+__global__ void k_fit(int n_leaves, const int* __restrict__ sorted, const float4* __restrict__ olo,
+                      const float4* __restrict__ ohi, const int* __restrict__ parent_leaf,
+                      const int* __restrict__ parent_int, const int* __restrict__ left, const int* __restrict__ right,
+                      float4* ilo, float4* ihi, int* visits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves) return;
+    int cur = parent_leaf[i];
+    while (cur >= 0) {
+        if (atomicAdd(&visits[cur], 1) == 0) return;  // the sibling subtree is not finished yet
+        __threadfence();
+        float4 l[2], h[2];
+        const int c[2] = {left[cur], right[cur]};
+        for (int k = 0; k < 2; k++) {
+            if (c[k] < 0) {
+                const int o = sorted[~c[k]];
+                l[k] = olo[o];
+                h[k] = ohi[o];
+            } else {
+                l[k] = __ldcg(&ilo[c[k]]);
+                h[k] = __ldcg(&ihi[c[k]]);
+            }
+        }
+        ilo[cur] = make_float4(fminf(l[0].x, l[1].x), fminf(l[0].y, l[1].y), fminf(l[0].z, l[1].z), 0.f);
+        ihi[cur] = make_float4(fmaxf(h[0].x, h[1].x), fmaxf(h[0].y, h[1].y), fmaxf(h[0].z, h[1].z), 0.f);
+        __threadfence();
+        cur = parent_int[cur];
+    }
+}
+
+struct TreeView {
+    const int *left, *right, *first, *last, *sorted;
+    const float4 *ilo, *ihi, *olo, *ohi;
+    int max_leaf;
+};
+
+__device__ __forceinline__ bool leaf_like(const TreeView& t, int c) {
+    return c < 0 || (t.last[c] - t.first[c] + 1) <= t.max_leaf;
+}
+__device__ __forceinline__ void child_box(const TreeView& t, int c, float4* l, float4* h) {
+    if (c < 0) {
+        const int o = t.sorted[~c];
+        *l = t.olo[o];
+        *h = t.ohi[o];
+    } else {
+        *l = t.ilo[c];
+        *h = t.ihi[c];
+    }
+}
+
+__device__ void write_wide(float4* nodes, int w, int nk, const float4* l, const float4* h, const int* ref) {
+    const float inf = __int_as_float(0x7f800000);
+    float v[6][4];
+    int ch[4];
+    for (int k = 0; k < 4; k++) {
+        const bool on = k < nk;
+        v[0][k] = on ? l[k].x : inf; v[1][k] = on ? h[k].x : -inf;
+        v[2][k] = on ? l[k].y : inf; v[3][k] = on ? h[k].y : -inf;
+        v[4][k] = on ? l[k].z : inf; v[5][k] = on ? h[k].z : -inf;
+        ch[k] = on ? ref[k] : kWideEmptyRef;
+    }
+    float4* p = nodes + (size_t)w * 8;
+    for (int r = 0; r < 6; r++) p[r] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+    p[6] = make_float4(__int_as_float(ch[0]), __int_as_float(ch[1]), __int_as_float(ch[2]), __int_as_float(ch[3]));
+    p[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// one thread per wide node of the current level
+__global__ void k_collapse(const Task* __restrict__ in, int n_in, Task* out, int* n_out, int* n_wide, int* max_depth,
+                           TreeView t, float4* nodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in) return;
+    const Task task = in[i];
+    int kids[4];
+    int nk = 2;
+    kids[0] = t.left[task.bnode];
+    kids[1] = t.right[task.bnode];
+    while (nk < 4) {  // open the inner child with the largest box
+        int pick = -1;
+        float pa = -1.f;
+        for (int k = 0; k < nk; k++) {
+            if (leaf_like(t, kids[k])) continue;
+            const float a = box_area(t.ilo[kids[k]], t.ihi[kids[k]]);
+            if (a > pa) { pa = a; pick = k; }
+        }
+        if (pick < 0) break;
+        const int c = kids[pick];
+        kids[pick] = t.left[c];
+        kids[nk++] = t.right[c];
+    }
+    float4 l[4], h[4];
+    int ref[4];
+    for (int k = 0; k < nk; k++) {
+        const int c = kids[k];
+        child_box(t, c, &l[k], &h[k]);
+        if (leaf_like(t, c)) {
+            const int f = c < 0 ? ~c : t.first[c];
+            const int cnt = c < 0 ? 1 : t.last[c] - t.first[c] + 1;
+            ref[k] = ~((f << 2) | (cnt - 1));
+        } else {
+            const int w = atomicAdd(n_wide, 1);
+            ref[k] = w;
+            const int o = atomicAdd(n_out, 1);
+            out[o] = Task{c, w, task.depth + 1};
+        }
+    }
+    write_wide(nodes, task.wide, nk, l, h, ref);
+    atomicMax(max_depth, task.depth);
+}
+
+// the whole tree is one leaf: a single node with one child
+__global__ void k_single_leaf(TreeView t, int n_rest, float4* nodes, float4* root_lo, float4* root_hi) {
+    if (threadIdx.x || blockIdx.x) return;
+    const float inf = __int_as_float(0x7f800000);
+    float4 l = make_float4(inf, inf, inf, 0.f), h = make_float4(-inf, -inf, -inf, 0.f);
+    for (int i = 0; i < n_rest; i++) {
+        const int o = t.sorted[i];
+        const float4 a = t.olo[o], b = t.ohi[o];
+        l = make_float4(fminf(l.x, a.x), fminf(l.y, a.y), fminf(l.z, a.z), 0.f);
+        h = make_float4(fmaxf(h.x, b.x), fmaxf(h.y, b.y), fmaxf(h.z, b.z), 0.f);
+    }
+    const int ref = ~((0 << 2) | (n_rest - 1));
+    write_wide(nodes, 0, 1, &l, &h, &ref);
+    *root_lo = l;
+    *root_hi = h;
+}
+
+__global__ void k_tri_records(const float4* __restrict__ objects, const int* __restrict__ sorted,
+                              const int* __restrict__ flags, int n_rest, float4* tris) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rest) return;
+    const int o = sorted[i];
+    const float4* op = objects + (size_t)o * 7;
+    const float4 a = __ldg(op), b = __ldg(op + 1), c = __ldg(op + 2);
+    float4* t = tris + (size_t)i * 3;
+    t[0] = make_float4(a.x, a.y, a.z, __int_as_float(o | (flags[o] & kTriNoDerive)));
+    t[1] = make_float4(b.x, b.y, b.z, 0.f);
+    t[2] = make_float4(c.x, c.y, c.z, 0.f);
+}
+
+int grid(long long n) { return (int)((n + kB - 1) / kB); }
+float __int_as_float_host(int i) {
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+
+// host mirror of the device's FADD.FTZ (single rounding, denormals flushed)
+float ftz(float r) { return std::fabs(r) < 1.17549435e-38f ? std::copysign(0.f, r) : r; }
+float sub_ftz(float a, float b) { return ftz(ftz(a) - ftz(b)); }
+
+struct Scratch {  // frees everything it allocated when it goes out of scope
+    std::vector<void*> ptrs;
+    ~Scratch() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <class T>
+    cudaError_t get(T** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *p = (T*)q;
+        return e;
+    }
+};
+
+}  // namespace
+
+#define BCU(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            if (err) *err = std::string(#call) + " failed: " + cudaGetErrorString(e_);                  \
+            return -1;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_nodes, int n_ref_nodes, int max_leaf,
+                          DeviceWideBvh* out, cudaStream_t s, std::string* err) {
+    max_leaf = std::max(1, std::min(4, max_leaf));
+    *out = DeviceWideBvh();
+    Scratch tmp;
+    cudaEvent_t ev0, ev1;
+    BCU(cudaEventCreate(&ev0));
+    BCU(cudaEventCreate(&ev1));
+    BCU(cudaEventRecord(ev0, s));
+
+    float4 *olo, *ohi;
+    int* flags;
+    Bounds* d_bounds;  // [0] scene, [1] centroids of the tree's objects
+    BCU(tmp.get(&olo, n));
+    BCU(tmp.get(&ohi, n));
+    BCU(tmp.get(&flags, n));
+    BCU(tmp.get(&d_bounds, 2));
+    k_init_bounds<<<1, 32, 0, s>>>(d_bounds, 2);
+
+    // 1. reference leaf box per object
+    if (d_ref_nodes && n_ref_nodes > 0) {
+        k_init_boxes<<<grid(n), kB, 0, s>>>(olo, ohi, n);
+        k_boxes_from_ref<<<grid(n_ref_nodes), kB, 0, s>>>(d_ref_nodes, n_ref_nodes, olo, ohi, n);
+    } else {
+        k_boxes_derived<<<grid(n), kB, 0, s>>>(d_objects, n, olo, ohi);
+    }
+    k_flags<<<grid(n), kB, 0, s>>>(d_objects, n, olo, ohi, flags, d_bounds);
+    Bounds hb[2];
+    BCU(cudaMemcpyAsync(hb, d_bounds, sizeof(Bounds), cudaMemcpyDeviceToHost, s));
+    BCU(cudaStreamSynchronize(s));
+    const int n_live = hb[0].count;
+    out->n_underivable = hb[0].aux;
+    const float inf = INFINITY;
+    out->top.root_lo = make_float4(inf, inf, inf, 0.f);
+    out->top.root_hi = make_float4(-inf, -inf, -inf, 0.f);
+    if (n_live == 0) {  // nothing can be hit: one empty node
+        BCU(cudaMalloc(&out->d_nodes, 128));
+        BCU(cudaMalloc(&out->d_tris, 48));
+        const float4 empty[8] = {make_float4(inf, inf, inf, inf), make_float4(-inf, -inf, -inf, -inf),
+                                 make_float4(inf, inf, inf, inf), make_float4(-inf, -inf, -inf, -inf),
+                                 make_float4(inf, inf, inf, inf), make_float4(-inf, -inf, -inf, -inf),
+                                 make_float4(__int_as_float_host(kWideEmptyRef), __int_as_float_host(kWideEmptyRef),
+                                             __int_as_float_host(kWideEmptyRef), __int_as_float_host(kWideEmptyRef)),
+                                 make_float4(0, 0, 0, 0)};
+        BCU(cudaMemcpyAsync(out->d_nodes, empty, 128, cudaMemcpyHostToDevice, s));
+        BCU(cudaStreamSynchronize(s));
+        out->n_nodes = 1;
+        return 0;
+    }
+
+    // 2. oversized primitives -> root-level list (same rule as the host builder: box area above
+    //    2 % of the scene box, the 12 largest, only for scenes of more than 16 primitives)
+    std::vector<int> top_ids;
+    {
+        const float dx = hb[0].mx[0] - hb[0].mn[0], dy = hb[0].mx[1] - hb[0].mn[1], dz = hb[0].mx[2] - hb[0].mn[2];
+        const float scene_area = std::max(2.f * (dx * dy + dy * dz + dz * dx), 1e-30f);
+        if (n_live > 16) {
+            int2* d_cand;
+            int* d_ncand;
+            BCU(tmp.get(&d_cand, kCandCap));
+            BCU(tmp.get(&d_ncand, 1));
+            BCU(cudaMemsetAsync(d_ncand, 0, 4, s));
+            k_select_top<<<grid(n), kB, 0, s>>>(olo, ohi, flags, n, 0.02f * scene_area, d_cand, d_ncand);
+            int n_cand = 0;
+            BCU(cudaMemcpyAsync(&n_cand, d_ncand, 4, cudaMemcpyDeviceToHost, s));
+            BCU(cudaStreamSynchronize(s));
+            if (n_cand > 0 && n_cand <= kCandCap) {
+                std::vector<int2> cand(n_cand);
+                BCU(cudaMemcpy(cand.data(), d_cand, sizeof(int2) * n_cand, cudaMemcpyDeviceToHost));
+                std::sort(cand.begin(), cand.end(), [](const int2& a, const int2& b) {
+                    float fa, fb;
+                    memcpy(&fa, &a.y, 4);
+                    memcpy(&fb, &b.y, 4);
+                    return fa != fb ? fa > fb : a.x < b.x;
+                });
+                for (int i = 0; i < n_cand && (int)top_ids.size() < kMaxTop; i++) top_ids.push_back(cand[i].x);
+            }
+            if ((int)top_ids.size() == n_live) top_ids.clear();
+        }
+    }
+    const int n_top = (int)top_ids.size();
+    if (n_top) {
+        int* d_ids;
+        BCU(tmp.get(&d_ids, kMaxTop));
+        BCU(cudaMemcpyAsync(d_ids, top_ids.data(), 4 * n_top, cudaMemcpyHostToDevice, s));
+        k_mark_top<<<1, 32, 0, s>>>(flags, d_ids, n_top);
+    }
+    out->n_top = n_top;
+
+    // 3. Morton order of the tree's objects
+    k_centroid_bounds<<<grid(n), kB, 0, s>>>(olo, ohi, flags, n, d_bounds + 1);
+    BCU(cudaMemcpyAsync(hb + 1, d_bounds + 1, sizeof(Bounds), cudaMemcpyDeviceToHost, s));
+    BCU(cudaStreamSynchronize(s));
+    const int n_rest = hb[1].count;
+    float3 cmin = make_float3(hb[1].mn[0], hb[1].mn[1], hb[1].mn[2]);
+    float3 scale;
+    {
+        const float e[3] = {hb[1].mx[0] - hb[1].mn[0], hb[1].mx[1] - hb[1].mn[1], hb[1].mx[2] - hb[1].mn[2]};
+        scale = make_float3(e[0] > 0.f ? 2097152.f / e[0] : 0.f, e[1] > 0.f ? 2097152.f / e[1] : 0.f,
+                            e[2] > 0.f ? 2097152.f / e[2] : 0.f);
+    }
+    unsigned long long *keys_a, *keys_b;
+    int *idx_a, *idx_b;
+    BCU(tmp.get(&keys_a, n));
+    BCU(tmp.get(&keys_b, n));
+    BCU(tmp.get(&idx_a, n));
+    BCU(tmp.get(&idx_b, n));
+    k_morton<<<grid(n), kB, 0, s>>>(olo, ohi, flags, n, cmin, scale, keys_a, idx_a);
+    {
+        size_t bytes = 0;
+        BCU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 64, s));
+        char* d_tmp;
+        BCU(tmp.get(&d_tmp, bytes));
+        BCU(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 64, s));
+    }
+    const unsigned long long* keys = keys_b;
+    const int* sorted = idx_b;  // the first n_rest entries are the tree's objects in Morton order
+
+    // 4. triangle records in leaf order
+    BCU(cudaMalloc(&out->d_tris, (size_t)std::max(n_rest, 1) * 48));
+    out->n_tris = n_rest;
+    k_tri_records<<<grid(n_rest), kB, 0, s>>>(d_objects, sorted, flags, n_rest, out->d_tris);
+
+    // 5. hierarchy, boxes, collapse
+    TreeView tv;
+    memset(&tv, 0, sizeof(tv));
+    tv.sorted = sorted;
+    tv.olo = olo;
+    tv.ohi = ohi;
+    tv.max_leaf = max_leaf;
+    float4* d_root;  // root_lo, root_hi
+    BCU(tmp.get(&d_root, 2));
+    if (n_rest <= max_leaf) {
+        BCU(cudaMalloc(&out->d_nodes, 128));
+        k_single_leaf<<<1, 32, 0, s>>>(tv, n_rest, out->d_nodes, d_root, d_root + 1);
+        out->n_nodes = 1;
+        out->depth = 1;
+    } else {
+        const int n_int = n_rest - 1;
+        int *left, *right, *parent_int, *parent_leaf, *first, *last, *visits;
+        float4 *ilo, *ihi;
+        BCU(tmp.get(&left, n_int));
+        BCU(tmp.get(&right, n_int));
+        BCU(tmp.get(&parent_int, n_int));
+        BCU(tmp.get(&parent_leaf, n_rest));
+        BCU(tmp.get(&first, n_int));
+        BCU(tmp.get(&last, n_int));
+        BCU(tmp.get(&visits, n_int));
+        BCU(tmp.get(&ilo, n_int));
+        BCU(tmp.get(&ihi, n_int));
+        BCU(cudaMemsetAsync(visits, 0, (size_t)n_int * 4, s));
+        k_hierarchy<<<grid(n_int), kB, 0, s>>>(keys, n_rest, left, right, parent_int, parent_leaf, first, last);
+        k_fit<<<grid(n_rest), kB, 0, s>>>(n_rest, sorted, olo, ohi, parent_leaf, parent_int, left, right, ilo, ihi, visits);
+        tv.left = left; tv.right = right; tv.first = first; tv.last = last; tv.ilo = ilo; tv.ihi = ihi;
+
+        float4* wide_tmp;  // a wide node consumes at least one internal node
+        Task *fr_a, *fr_b;
+        int* d_cnt;  // [0] next-level tasks, [1] wide nodes allocated, [2] depth
+        BCU(tmp.get(&wide_tmp, (size_t)n_int * 8));
+        BCU(tmp.get(&fr_a, n_int));
+        BCU(tmp.get(&fr_b, n_int));
+        BCU(tmp.get(&d_cnt, 4));
+        const Task root_task = {0, 0, 1};
+        const int init_cnt[4] = {0, 1, 0, 0};
+        BCU(cudaMemcpyAsync(fr_a, &root_task, sizeof(Task), cudaMemcpyHostToDevice, s));
+        BCU(cudaMemcpyAsync(d_cnt, init_cnt, sizeof(init_cnt), cudaMemcpyHostToDevice, s));
+        int n_in = 1;
+        int h_cnt[4];
+        for (int level = 0; n_in > 0; level++) {
+            if (level > 512) {
+                if (err) *err = "device BVH collapse did not terminate";
+                return -1;
+            }
+            k_collapse<<<grid(n_in), kB, 0, s>>>(fr_a, n_in, fr_b, d_cnt, d_cnt + 1, d_cnt + 2, tv, wide_tmp);
+            BCU(cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
+            BCU(cudaStreamSynchronize(s));
+            n_in = h_cnt[0];
+            BCU(cudaMemsetAsync(d_cnt, 0, 4, s));
+            std::swap(fr_a, fr_b);
+        }
+        out->n_nodes = h_cnt[1];
+        out->depth = h_cnt[2];
+        BCU(cudaMalloc(&out->d_nodes, (size_t)out->n_nodes * 128));
+        BCU(cudaMemcpyAsync(out->d_nodes, wide_tmp, (size_t)out->n_nodes * 128, cudaMemcpyDeviceToDevice, s));
+        BCU(cudaMemcpyAsync(d_root, ilo, 16, cudaMemcpyDeviceToDevice, s));
+        BCU(cudaMemcpyAsync(d_root + 1, ihi, 16, cudaMemcpyDeviceToDevice, s));
+    }
+    float4 h_root[2];
+    BCU(cudaMemcpyAsync(h_root, d_root, 32, cudaMemcpyDeviceToHost, s));
+
+    // 6. the root-level list, on the host (at most 12 primitives)
+    TopPrims& tp = out->top;
+    memset(&tp, 0, sizeof(tp));
+    tp.n = n_top;
+    for (int i = 0; i < n_top; i++) {
+        float4 ob[3], bl, bh;
+        int f;
+        BCU(cudaMemcpyAsync(ob, d_objects + (size_t)top_ids[i] * 7, 48, cudaMemcpyDeviceToHost, s));
+        BCU(cudaMemcpyAsync(&bl, olo + top_ids[i], 16, cudaMemcpyDeviceToHost, s));
+        BCU(cudaMemcpyAsync(&bh, ohi + top_ids[i], 16, cudaMemcpyDeviceToHost, s));
+        BCU(cudaMemcpyAsync(&f, flags + top_ids[i], 4, cudaMemcpyDeviceToHost, s));
+        BCU(cudaStreamSynchronize(s));
+        tp.v0[i] = make_float4(ob[0].x, ob[0].y, ob[0].z, __int_as_float_host(top_ids[i] | (f & kTriNoDerive)));
+        tp.e1[i] = make_float4(sub_ftz(ob[1].x, ob[0].x), sub_ftz(ob[1].y, ob[0].y), sub_ftz(ob[1].z, ob[0].z), 0.f);
+        tp.e2[i] = make_float4(sub_ftz(ob[2].x, ob[0].x), sub_ftz(ob[2].y, ob[0].y), sub_ftz(ob[2].z, ob[0].z), 0.f);
+        tp.bmin[i] = make_float4(bl.x, bl.y, bl.z, 0.f);
+        tp.bmax[i] = make_float4(bh.x, bh.y, bh.z, 0.f);
+        const float ext[3] = {bh.x - bl.x, bh.y - bl.y, bh.z - bl.z};
+        int ax = 0;
+        for (int k = 1; k < 3; k++)
+            if (ext[k] < ext[ax]) ax = k;
+        tp.thin_axis[i] = ax;
+    }
+    BCU(cudaEventRecord(ev1, s));
+    BCU(cudaStreamSynchronize(s));
+    tp.root_lo = make_float4(h_root[0].x, h_root[0].y, h_root[0].z, 0.f);
+    tp.root_hi = make_float4(h_root[1].x, h_root[1].y, h_root[1].z, 0.f);
+    BCU(cudaEventElapsedTime(&out->build_ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    BCU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace trt

@@ -64,7 +64,7 @@ struct WideCounts {
 
 constexpr int kWideEmptyRef = 0x7fffffff;
 constexpr int kSmemNodeStride = 144;  // bytes between staged nodes in shared memory (128 + 16 pad)
-constexpr int kSpillEntries = 48;  // logical node stack bound: 3 * wide depth + 1 (checked at upload)
+constexpr int kSpillEntries = 128;  // logical node stack bound: 3 * wide depth + 1 (checked at upload)
 constexpr float kCullSlack = 1.0005f;
 constexpr int kTriIdMask = 0x3fffffff;
 constexpr int kTriNoDerive = 0x40000000;  // leaf box cannot be re-derived from the vertices: replay
@@ -385,7 +385,7 @@ TRT_DEV bool resolve_hit(const SceneDev& sc, const F3 o, const F3 d, float& t, i
         float entry;
         ok = leaf_box_reach(bmin, bmax, o, inv, inv.x < 0.f, inv.y < 0.f, inv.z < 0.f, &entry) && entry < t;
     }
-    if (ok) return false;
+    if (ok || sc.n_ref_nodes == 0) return false;  // no reference tree uploaded: nothing to replay through
     Ray r;
     r.o = o;
     r.d = d;
