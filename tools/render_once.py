@@ -23,7 +23,8 @@ o = trt.default_opts(traversal=trav, pool_paths=pool)
 if warm:
     ctx.render(acc, w, h, 1, warm, cam, o); ctx.synchronize()
 ctx.reset_counters()
-ot = trt.default_opts(traversal=trav, pool_paths=pool, time_kernels=timed)
+cnt = int(os.environ.get('TRT_COUNT', '0'))
+ot = trt.default_opts(traversal=trav, pool_paths=pool, time_kernels=timed, count_rays=cnt)
 ctx.render(acc, w, h, 1 + warm, spp, cam, ot); ctx.synchronize()
 ms = ctx.last_render_ms()
 c = ctx.counters()
@@ -32,6 +33,10 @@ line = f"ms/spp {ms / spp:.3f} Mrays/s {rays / ms / 1e3:.0f} rays/sample {rays /
 if timed:
     k = ctx.kernel_times()
     line += " | " + " ".join(f"{n[:-3]} {k[n]:.1f}" for n in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms"))
+if cnt:
+    line += (f" | closest: nodes/ray {c['nodes_closest'] / max(c['closest_rays'], 1):.2f} tris/ray {c['tris_closest'] / max(c['closest_rays'], 1):.2f}"
+             f" shadow: nodes/ray {(c['nodes_fetched'] - c['nodes_closest']) / max(c['shadow_rays'], 1):.2f} tris/ray {(c['tris_tested'] - c['tris_closest']) / max(c['shadow_rays'], 1):.2f}"
+             f" rays c/s {c['closest_rays']}/{c['shadow_rays']}")
 inf = ctx.scene_info()
 line += f" | builder {inf['builder']} build_ms {inf['build_ms']:.1f} wide_nodes {inf['n_wide_nodes']} depth {inf['wide_depth']} host_prep_s {host_s:.1f}"
 print(line, "mean", float(acc.view(-1, 4)[:, :3].mean()) / (spp + warm))

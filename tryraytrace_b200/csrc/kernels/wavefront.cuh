@@ -19,7 +19,7 @@ namespace trt {
 
 enum { SLOT_DEAD = 0, SLOT_ACTIVE = 1, SLOT_FINISH = 2 };
 
-// Path slot, SoA: 136 bytes per slot over all arrays.
+// Path slot, SoA: 128 bytes per slot over all arrays.
 struct PoolView {
     float4* ray_o;   // origin.xyz, length of the slot's shadow ray (it starts at the same point)
     float4* ray_d;   // direction.xyz, flags (int bits): state | depth << 8 | prev_mode << 16
