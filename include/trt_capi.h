@@ -65,6 +65,8 @@ typedef struct {
     uint64_t kernel_launches;   /* kernels launched by the library */
     uint64_t nodes_closest;     /* node records fetched by closest-hit queries only */
     uint64_t tris_closest;      /* triangle tests by closest-hit queries only */
+    uint64_t tree_closest;      /* closest-hit queries that entered the tree (count_rays builds, FAST mode) */
+    uint64_t tree_shadow;       /* any-hit queries that entered the tree */
 } trt_counters;
 
 /* Device time of the last trt_render per kernel family, from CUDA events recorded on the

@@ -36,7 +36,7 @@ if timed:
 if cnt:
     line += (f" | closest: nodes/ray {c['nodes_closest'] / max(c['closest_rays'], 1):.2f} tris/ray {c['tris_closest'] / max(c['closest_rays'], 1):.2f}"
              f" shadow: nodes/ray {(c['nodes_fetched'] - c['nodes_closest']) / max(c['shadow_rays'], 1):.2f} tris/ray {(c['tris_tested'] - c['tris_closest']) / max(c['shadow_rays'], 1):.2f}"
-             f" rays c/s {c['closest_rays']}/{c['shadow_rays']}")
+             f" rays c/s {c['closest_rays']}/{c['shadow_rays']} tree fraction c/s {c['tree_closest'] / max(c['closest_rays'], 1):.3f}/{c['tree_shadow'] / max(c['shadow_rays'], 1):.3f}")
 inf = ctx.scene_info()
 line += f" | builder {inf['builder']} build_ms {inf['build_ms']:.1f} wide_nodes {inf['n_wide_nodes']} depth {inf['wide_depth']} host_prep_s {host_s:.1f}"
 print(line, "mean", float(acc.view(-1, 4)[:, :3].mean()) / (spp + warm))

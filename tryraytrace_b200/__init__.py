@@ -55,7 +55,7 @@ class Opts(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "closest_rays", "shadow_rays", "nodes_fetched",
                                           "tris_tested", "replays", "iterations", "kernel_launches",
-                                          "nodes_closest", "tris_closest")]
+                                          "nodes_closest", "tris_closest", "tree_closest", "tree_shadow")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -758,6 +758,8 @@ int trt_get_counters(trt_ctx* c, trt_counters* out) {
     out->kernel_launches = c->launches;
     out->nodes_closest = hc.cnt_nodes_closest;
     out->tris_closest = hc.cnt_tris_closest;
+    out->tree_closest = hc.cnt_tree_closest;
+    out->tree_shadow = hc.cnt_tree_shadow;
     return 0;
 }
 

@@ -229,6 +229,19 @@ void build_wide_bvh(const Object* objects, int n_objects, const LinearBVHNode* r
                 top.push_back(by_area[i]);
                 is_top[by_area[i]] = 1;
             }
+        // Light sources (emission above the reference's listing threshold, src/main.cpp:93) join the
+        // root-level list when there are only a few of them: every shadow ray ends just short of a
+        // light, so a light inside the tree stretches the tree's bounding box over all of them and
+        // sends every shadow ray (and most closest-hit rays) into the tree for nothing.
+        if (live.size() > 16) {
+            std::vector<int> emitters;
+            for (int o : live) {
+                const Object& ob = objects[o];
+                if (!is_top[o] && (ob.emission.x > 0.1f || ob.emission.y > 0.1f || ob.emission.z > 0.1f)) emitters.push_back(o);
+            }
+            if (emitters.size() <= (size_t)kMaxTopLights && top.size() + emitters.size() <= max_top)
+                for (int o : emitters) { top.push_back(o); is_top[o] = 1; }
+        }
         for (int o : live)
             if (!is_top[o]) rest.push_back(o);
         if (rest.empty()) { rest = live; top.clear(); }

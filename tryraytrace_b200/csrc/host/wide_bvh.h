@@ -51,6 +51,7 @@ struct LeafBox {  // 32 bytes
 };
 
 constexpr int kMaxTopPrims = 12;
+constexpr int kMaxTopLights = 4;  // light sources lifted into the root-level list, when there are at most this many
 
 // A root-level primitive: vertices as (v0, e1 = v1 - v0, e2 = v2 - v0) with the single FTZ
 // rounding the reference applies per test (reference src/renderer.cu:239-240), and its

@@ -19,6 +19,7 @@ namespace {
 constexpr int kB = 256;
 constexpr int kFlagValid = 1, kFlagTop = 2;  // kTriNoDerive (bit 30) rides in the same word
 constexpr int kCandCap = 1024;
+constexpr int kLightCap = 4;  // host/wide_bvh.h kMaxTopLights
 
 struct Bounds {
     float mn[3], mx[3];
@@ -147,14 +148,23 @@ __device__ __forceinline__ float box_area(float4 l, float4 h) {
     return 2.f * (dx * dy + dy * dz + dz * dx);
 }
 
-__global__ void k_select_top(const float4* __restrict__ lo, const float4* __restrict__ hi, const int* __restrict__ flags,
-                             int n, float thr_area, int2* cand, int* n_cand) {
+// candidates for the root-level list: oversized boxes, and light sources (emission above the
+// reference's listing threshold, src/main.cpp:93; see host/wide_bvh.cpp for why)
+__global__ void k_select_top(const float4* __restrict__ objects, const float4* __restrict__ lo,
+                             const float4* __restrict__ hi, const int* __restrict__ flags, int n, float thr_area,
+                             int2* cand, int* n_cand, int* lights, int* n_lights) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !(flags[i] & kFlagValid)) return;
     const float a = box_area(lo[i], hi[i]);
     if (a >= thr_area) {
         const int k = atomicAdd(n_cand, 1);
         if (k < kCandCap) cand[k] = make_int2(i, __float_as_int(a));
+        return;
+    }
+    const float4 e = __ldg(objects + (size_t)i * 7 + 4);
+    if (e.x > 0.1f || e.y > 0.1f || e.z > 0.1f) {
+        const int k = atomicAdd(n_lights, 1);
+        if (k < kLightCap) lights[k] = i;
     }
 }
 
@@ -482,14 +492,17 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
         const float scene_area = std::max(2.f * (dx * dy + dy * dz + dz * dx), 1e-30f);
         if (n_live > 16) {
             int2* d_cand;
-            int* d_ncand;
+            int *d_ncand, *d_lights;  // d_ncand[0] oversized candidates, d_ncand[1] light sources
             BCU(tmp.get(&d_cand, kCandCap));
-            BCU(tmp.get(&d_ncand, 1));
-            BCU(cudaMemsetAsync(d_ncand, 0, 4, s));
-            k_select_top<<<grid(n), kB, 0, s>>>(olo, ohi, flags, n, 0.02f * scene_area, d_cand, d_ncand);
-            int n_cand = 0;
-            BCU(cudaMemcpyAsync(&n_cand, d_ncand, 4, cudaMemcpyDeviceToHost, s));
+            BCU(tmp.get(&d_ncand, 2));
+            BCU(tmp.get(&d_lights, kLightCap));
+            BCU(cudaMemsetAsync(d_ncand, 0, 8, s));
+            k_select_top<<<grid(n), kB, 0, s>>>(d_objects, olo, ohi, flags, n, 0.02f * scene_area, d_cand, d_ncand,
+                                                d_lights, d_ncand + 1);
+            int h_n[2] = {0, 0};
+            BCU(cudaMemcpyAsync(h_n, d_ncand, 8, cudaMemcpyDeviceToHost, s));
             BCU(cudaStreamSynchronize(s));
+            const int n_cand = h_n[0], n_emit = h_n[1];
             if (n_cand > 0 && n_cand <= kCandCap) {
                 std::vector<int2> cand(n_cand);
                 BCU(cudaMemcpy(cand.data(), d_cand, sizeof(int2) * n_cand, cudaMemcpyDeviceToHost));
@@ -500,6 +513,12 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
                     return fa != fb ? fa > fb : a.x < b.x;
                 });
                 for (int i = 0; i < n_cand && (int)top_ids.size() < kMaxTop; i++) top_ids.push_back(cand[i].x);
+            }
+            if (n_emit > 0 && n_emit <= kLightCap && (int)top_ids.size() + n_emit <= kMaxTop) {
+                int ids[kLightCap];
+                BCU(cudaMemcpy(ids, d_lights, 4 * n_emit, cudaMemcpyDeviceToHost));
+                std::sort(ids, ids + n_emit);
+                for (int i = 0; i < n_emit; i++) top_ids.push_back(ids[i]);
             }
             if ((int)top_ids.size() == n_live) top_ids.clear();
         }

@@ -75,6 +75,7 @@ __global__ void k_reset_counters(Control* ctl) {
     ctl->cnt_samples = ctl->cnt_closest = ctl->cnt_shadow = ctl->cnt_nodes = ctl->cnt_tris = 0;
     ctl->cnt_replays = ctl->cnt_iterations = 0;
     ctl->cnt_nodes_closest = ctl->cnt_tris_closest = 0;
+    ctl->cnt_tree_closest = ctl->cnt_tree_shadow = 0;
 }
 
 __global__ void k_reset_cursors(Control* ctl) {
@@ -432,6 +433,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     st.nspill = 0;
     st.cur = kWideEmptyRef;
     WideCounts wc = {0, 0};
+    unsigned wc_tree = 0;
     bool has = false;
     int slot = -1;
     int qn = 0;  // warp-uniform: entries in the tree-ray queue
@@ -460,6 +462,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
                 q_s[qi] = my_slot;
             }
             qn += __popc(m);
+            if (COUNT && lane == 0) wc_tree += __popc(m);
             fd.fresh = false;
             __syncwarp();
         }
@@ -508,6 +511,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         warp_add(&ctl->cnt_tris, wc.tris);
         warp_add(&ctl->cnt_nodes_closest, wc.nodes);
         warp_add(&ctl->cnt_tris_closest, wc.tris);
+        warp_add(&ctl->cnt_tree_closest, wc_tree);
     }
 }
 
@@ -550,6 +554,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     st.nspill = 0;
     st.occluded = false;
     WideCounts wc = {0, 0};
+    unsigned wc_tree = 0;
     bool has = false;
     int slot = -1;
     int qn = 0;
@@ -576,6 +581,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
                 q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f(my_slot));
             }
             qn += __popc(m);
+            if (COUNT && lane == 0) wc_tree += __popc(m);
             fd.fresh = false;
             __syncwarp();
         }
@@ -623,6 +629,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     if (COUNT) {
         warp_add(&ctl->cnt_nodes, wc.nodes);
         warp_add(&ctl->cnt_tris, wc.tris);
+        warp_add(&ctl->cnt_tree_shadow, wc_tree);
     }
 }
 

@@ -48,6 +48,7 @@ struct Control {
     unsigned long long cnt_samples, cnt_closest, cnt_shadow, cnt_replays, cnt_iterations;
     unsigned long long cnt_nodes, cnt_tris;                // all queries (COUNT builds only)
     unsigned long long cnt_nodes_closest, cnt_tris_closest;  // closest-hit queries only
+    unsigned long long cnt_tree_closest, cnt_tree_shadow;    // queries that entered the tree (COUNT builds only)
 };
 
 // Per-job constants handed to the kernels by value.
