@@ -305,6 +305,29 @@ void fill_job(trt_ctx* c, JobParams& job, float* d_accum, int w, int h, int firs
     job.accum = d_accum;
 }
 
+// Sorts the root-level list by the axis on which each leaf box is thinnest and fills the per-axis
+// counts and planes the shadow top phase reads (kernels/common.cuh TopPrims).
+void finalize_top(TopPrims& tp) {
+    struct Item { float4 v0, e1, e2, bmin, bmax; int axis; };
+    std::vector<Item> items(tp.n);
+    for (int i = 0; i < tp.n; i++) {
+        const float ext[3] = {tp.bmax[i].x - tp.bmin[i].x, tp.bmax[i].y - tp.bmin[i].y, tp.bmax[i].z - tp.bmin[i].z};
+        int ax = 0;
+        for (int k = 1; k < 3; k++)
+            if (ext[k] < ext[ax]) ax = k;
+        items[i] = Item{tp.v0[i], tp.e1[i], tp.e2[i], tp.bmin[i], tp.bmax[i], ax};
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.axis < b.axis; });
+    tp.n_axis[0] = tp.n_axis[1] = tp.n_axis[2] = 0;
+    for (int i = 0; i < tp.n; i++) {
+        const Item& it = items[i];
+        tp.v0[i] = it.v0; tp.e1[i] = it.e1; tp.e2[i] = it.e2; tp.bmin[i] = it.bmin; tp.bmax[i] = it.bmax;
+        tp.thin_lo[i] = it.axis == 0 ? it.bmin.x : (it.axis == 1 ? it.bmin.y : it.bmin.z);
+        tp.thin_hi[i] = it.axis == 0 ? it.bmax.x : (it.axis == 1 ? it.bmax.y : it.bmax.z);
+        tp.n_axis[it.axis]++;
+    }
+}
+
 int check_opts(const trt_opts* in, trt_opts* o) {
     if (in) *o = *in;
     else trt_default_opts(o);
@@ -558,16 +581,13 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
             tp.e2[i] = make_float4(t.e2[0], t.e2[1], t.e2[2], 0.f);
             tp.bmin[i] = make_float4(t.mn[0], t.mn[1], t.mn[2], 0.f);
             tp.bmax[i] = make_float4(t.mx[0], t.mx[1], t.mx[2], 0.f);
-            int ax = 0;
-            for (int k = 1; k < 3; k++)
-                if (t.mx[k] - t.mn[k] < t.mx[ax] - t.mn[ax]) ax = k;
-            tp.thin_axis[i] = ax;
         }
         tp.root_lo = make_float4(wb.root_mn[0], wb.root_mn[1], wb.root_mn[2], 0.f);
         tp.root_hi = make_float4(wb.root_mx[0], wb.root_mx[1], wb.root_mx[2], 0.f);
         n_wide = (int)wb.nodes.size(); n_tris = (int)wb.tris.size(); n_top = wb.n_top_prims; depth = wb.depth;
         n_underivable = wb.n_underivable;
     }
+    finalize_top(tp);
     if (3 * depth + 1 > kWideStackEntries) {
         free_scene(c);
         return fail(TRT_ERR_ARG, "wide BVH depth %d exceeds the traversal stack", depth);

@@ -650,11 +650,6 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
         tp.e2[i] = make_float4(sub_ftz(ob[2].x, ob[0].x), sub_ftz(ob[2].y, ob[0].y), sub_ftz(ob[2].z, ob[0].z), 0.f);
         tp.bmin[i] = make_float4(bl.x, bl.y, bl.z, 0.f);
         tp.bmax[i] = make_float4(bh.x, bh.y, bh.z, 0.f);
-        const float ext[3] = {bh.x - bl.x, bh.y - bl.y, bh.z - bl.z};
-        int ax = 0;
-        for (int k = 1; k < 3; k++)
-            if (ext[k] < ext[ax]) ax = k;
-        tp.thin_axis[i] = ax;
     }
     BCU(cudaEventRecord(ev1, s));
     BCU(cudaStreamSynchronize(s));

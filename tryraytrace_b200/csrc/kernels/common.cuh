@@ -88,9 +88,12 @@ struct TopPrims {
     float4 bmin[kMaxTop];  // reference leaf box as uploaded
     float4 bmax[kMaxTop];
     float4 root_lo, root_hi;
-    int thin_axis[kMaxTop];  // axis on which the leaf box is thinnest
+    // The list is sorted by the axis on which each leaf box is thinnest: primitives [0, n_axis[0]) are
+    // thinnest along x, the next n_axis[1] along y, the rest along z; thin_lo / thin_hi are the
+    // box planes on that axis (the shadow top phase tests them first, traverse_fast.cuh).
+    float thin_lo[kMaxTop], thin_hi[kMaxTop];
+    int n_axis[3];
     int n;
-    int _pad[3];
 };
 
 struct RenderConsts {

@@ -538,26 +538,46 @@ TRT_DEV void shadow_begin(ShadowRay& s, const float4 o4, const float4 d4, uint32
 // "max(t1,t2) > 0.001 and min(t1,t2) < max_dist" is NECESSARY for the box to pass.  A ray that
 // stays inside the room fails it for every wall (the flat wall boxes are 2e-3 thick), at a
 // fifth of the cost of the triangle test; the full tests run only for warps where some lane
-// passes it (or has a non-finite reciprocal).  Lanes whose slot holds no shadow ray (`live` false)
-// take no part in the decision.
+// passes it.  A warp in which some live lane has a non-finite reciprocal runs the full tests.
+// Lanes whose slot holds no shadow ray (`live` false) take no part in the decision.
+// one root-level primitive of the shadow top phase; oa / ia are the ray's origin and reciprocal
+// direction on the primitive's thin axis
+TRT_DEV bool top_shadow_prim(const TopPrims& top, int p, float oa, float ia, const F3 o, const F3 d, const F3 inv,
+                             float max_dist, float t_hi, bool take) {
+    const float t1 = p_mul(p_sub(top.thin_lo[p], oa), ia), t2 = p_mul(p_sub(top.thin_hi[p], oa), ia);
+    const bool maybe = take & (fmaxf(t1, t2) > 0.001f) & (fminf(t1, t2) < max_dist);
+    bool occluded = false;
+    if (__any_sync(0xffffffffu, maybe)) {
+        const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
+        const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
+        occluded = t > 0.001f && t < t_hi && ref_slab(top.bmin[p], top.bmax[p], o, inv, 0.001f, max_dist);
+    }
+    return occluded;
+}
+
 TRT_DEV int top_shadow(const TopPrims& top, const F3 o, const F3 d, float max_dist, bool live) {
     const F3 inv = f3(p_rcp(d.x), p_rcp(d.y), p_rcp(d.z));  // raw reciprocal, reference :276
     const float t_hi = p_sub(max_dist, 0.001f);
     const float kInf = __int_as_float(0x7f800000);
     const bool finite = fabsf(inv.x) < kInf && fabsf(inv.y) < kInf && fabsf(inv.z) < kInf;
     bool occluded = false;
+    if (__all_sync(0xffffffffu, finite | !live)) {
+        // the list is sorted by thin axis, so each loop reads the ray's component from a fixed register
+        int p = 0;
 #pragma unroll 1
-    for (int p = 0; p < top.n; p++) {
-        const int ax = top.thin_axis[p];
-        const float4 lo4 = top.bmin[p], hi4 = top.bmax[p];
-        const float pl = ax == 0 ? lo4.x : (ax == 1 ? lo4.y : lo4.z), ph = ax == 0 ? hi4.x : (ax == 1 ? hi4.y : hi4.z);
-        const float oa = ax == 0 ? o.x : (ax == 1 ? o.y : o.z), ia = ax == 0 ? inv.x : (ax == 1 ? inv.y : inv.z);
-        const float t1 = p_mul(p_sub(pl, oa), ia), t2 = p_mul(p_sub(ph, oa), ia);
-        const bool maybe = live && (!finite || (fmaxf(t1, t2) > 0.001f && fminf(t1, t2) < max_dist));
-        if (__any_sync(0xffffffffu, maybe)) {
+        for (const int e = top.n_axis[0]; p < e; p++) occluded |= top_shadow_prim(top, p, o.x, inv.x, o, d, inv, max_dist, t_hi, live);
+#pragma unroll 1
+        for (const int e = top.n_axis[0] + top.n_axis[1]; p < e; p++) occluded |= top_shadow_prim(top, p, o.y, inv.y, o, d, inv, max_dist, t_hi, live);
+#pragma unroll 1
+        for (; p < top.n; p++) occluded |= top_shadow_prim(top, p, o.z, inv.z, o, d, inv, max_dist, t_hi, live);
+    } else {
+        // some lane has an infinite reciprocal (a zero direction component): a NaN could defeat the
+        // one-axis argument, so the warp runs the full tests for every primitive
+#pragma unroll 1
+        for (int p = 0; p < top.n; p++) {
             const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
             const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
-            if (t > 0.001f && t < t_hi && ref_slab(lo4, hi4, o, inv, 0.001f, max_dist)) occluded = true;
+            if (t > 0.001f && t < t_hi && ref_slab(top.bmin[p], top.bmax[p], o, inv, 0.001f, max_dist)) occluded = true;
         }
     }
     if (occluded) return 1;
