@@ -47,7 +47,6 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kFrameChunk = 64;       // frames per wavefront job (bounds the column-vector table)
 constexpr int kBatchIterations = 16;  // iterations issued between completion polls
-constexpr int kDefaultPool = 1 << 20;
 constexpr int kWideStackEntries = 128;  // kernels/traverse_fast.cuh kSpillEntries
 constexpr int kAutoDeviceBuildAbove = 1 << 18;  // TRT_BUILD_AUTO: objects above which the device builder is used
 
@@ -352,7 +351,15 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if ((long long)o.seed_base + first < 0) return fail(TRT_ERR_ARG, "negative RNG seed");
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_rng_tables(c, w, h)) return rc;
-    if (int rc = ensure_pool(c, o.pool_paths ? o.pool_paths : kDefaultPool)) return rc;
+    // pool_paths = 0: size the pool to the job -- about a sixth of its samples in flight, between
+    // 256 Ki and 4 Mi slots (B200 sweeps: 1 Mi is best for the 4.9 M samples of C1, 4 Mi from C2 up)
+    int pool_paths = o.pool_paths;
+    if (pool_paths == 0) {
+        const unsigned long long want = (unsigned long long)w * h * (unsigned long long)n_frames / 6;
+        pool_paths = 256 << 10;
+        while (pool_paths < (4 << 20) && (unsigned long long)pool_paths < want) pool_paths <<= 1;
+    }
+    if (int rc = ensure_pool(c, pool_paths)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
     c->marks_used = 0;
