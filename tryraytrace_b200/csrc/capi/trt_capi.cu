@@ -559,8 +559,10 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
         if (const char* e = getenv("TRT_MAX_LEAF")) max_leaf = std::max(1, std::min(4, atoi(e)));
         DeviceWideBvh dw;
         std::string err;
-        if (build_wide_bvh_device(c->d_objects, n_objects, c->d_ref_nodes, have_ref ? n_nodes : 0, max_leaf, &dw, c->stream,
-                                  &err) != 0) {
+        bool top_sah = true;
+        if (const char* e = getenv("TRT_TOP_SAH")) top_sah = atoi(e) != 0;
+        if (build_wide_bvh_device(c->d_objects, n_objects, c->d_ref_nodes, have_ref ? n_nodes : 0, max_leaf, top_sah, &dw,
+                                  c->stream, &err) != 0) {
             cudaFree(dw.d_nodes);
             cudaFree(dw.d_tris);
             cudaGetLastError();

@@ -287,6 +287,39 @@ __global__ void k_fit(int n_leaves, const int* __restrict__ sorted, const float4
     }
 }
 
+// Cluster roots of the LBVH: the subtrees of at most `cmax` primitives whose parent is larger.
+// The host builds a SAH tree over their boxes (the upper levels, where Morton splits are poorest);
+// below a cluster root the LBVH is kept.  ref >= 0 internal node, < 0 leaf ~index.
+struct Cluster {
+    float4 lo, hi;  // lo.w carries the node reference (int bits)
+};
+__global__ void k_clusters(int n_leaves, int cmax, const int* __restrict__ first, const int* __restrict__ last,
+                           const int* __restrict__ parent_int, const int* __restrict__ parent_leaf,
+                           const int* __restrict__ sorted, const float4* __restrict__ olo, const float4* __restrict__ ohi,
+                           const float4* __restrict__ ilo, const float4* __restrict__ ihi, Cluster* out, int cap, int* n_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_int = n_leaves - 1;
+    if (i >= n_int + n_leaves) return;
+    int ref, parent, count;
+    if (i < n_int) {
+        ref = i;
+        parent = parent_int[i];
+        count = last[i] - first[i] + 1;
+    } else {
+        ref = ~(i - n_int);
+        parent = parent_leaf[i - n_int];
+        count = 1;
+    }
+    if (count > cmax || parent < 0) return;
+    if (last[parent] - first[parent] + 1 <= cmax) return;  // the parent is inside a cluster already
+    const int k = atomicAdd(n_out, 1);
+    if (k >= cap) return;
+    float4 l, h;
+    if (ref >= 0) { l = ilo[ref]; h = ihi[ref]; } else { const int o = sorted[~ref]; l = olo[o]; h = ohi[o]; }
+    out[k].lo = make_float4(l.x, l.y, l.z, __int_as_float(ref));
+    out[k].hi = h;
+}
+
 struct TreeView {
     const int *left, *right, *first, *last, *sorted;
     const float4 *ilo, *ihi, *olo, *ohi;
@@ -408,6 +441,100 @@ float __int_as_float_host(int i) {
 float ftz(float r) { return std::fabs(r) < 1.17549435e-38f ? std::copysign(0.f, r) : r; }
 float sub_ftz(float a, float b) { return ftz(ftz(a) - ftz(b)); }
 
+// Binned SAH (16 bins) over the cluster boxes, one cluster per leaf.  Output: binary nodes with
+// children >= 0 = top node index, < 0 = ~cluster index; node 0 is the root.
+struct TopNode {
+    float lo[3], hi[3];
+    int left, right;
+};
+struct TopSah {
+    const std::vector<Cluster>& c;
+    std::vector<int> order;
+    std::vector<TopNode> nodes;
+    explicit TopSah(const std::vector<Cluster>& cl) : c(cl), order(cl.size()) {
+        for (size_t i = 0; i < cl.size(); i++) order[i] = (int)i;
+        nodes.reserve(cl.size());
+    }
+    static float area(const float* lo, const float* hi) {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return (dx < 0 || dy < 0 || dz < 0) ? 0.f : 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+    static void grow(float* lo, float* hi, const Cluster& k) {
+        lo[0] = std::min(lo[0], k.lo.x); lo[1] = std::min(lo[1], k.lo.y); lo[2] = std::min(lo[2], k.lo.z);
+        hi[0] = std::max(hi[0], k.hi.x); hi[1] = std::max(hi[1], k.hi.y); hi[2] = std::max(hi[2], k.hi.z);
+    }
+    static float centroid(const Cluster& k, int a) {
+        return a == 0 ? 0.5f * (k.lo.x + k.hi.x) : (a == 1 ? 0.5f * (k.lo.y + k.hi.y) : 0.5f * (k.lo.z + k.hi.z));
+    }
+    // returns the child reference of the subtree over order[first, first + count)
+    int build(int first, int count) {
+        if (count == 1) return ~order[first];
+        const int self = (int)nodes.size();
+        nodes.emplace_back();
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = first; i < first + count; i++) {
+            const Cluster& k = c[order[i]];
+            grow(lo, hi, k);
+            for (int a = 0; a < 3; a++) { const float x = centroid(k, a); clo[a] = std::min(clo[a], x); chi[a] = std::max(chi[a], x); }
+        }
+        constexpr int B = 16;
+        float best = INFINITY;
+        int best_axis = -1, best_split = -1;
+        for (int a = 0; a < 3; a++) {
+            const float ext = chi[a] - clo[a];
+            if (!(ext > 0.f)) continue;
+            float blo[B][3], bhi[B][3];
+            int bc[B];
+            for (int b = 0; b < B; b++) { for (int k = 0; k < 3; k++) { blo[b][k] = INFINITY; bhi[b][k] = -INFINITY; } bc[b] = 0; }
+            const float scale = B / ext;
+            for (int i = first; i < first + count; i++) {
+                const Cluster& k = c[order[i]];
+                const int b = std::min(std::max((int)((centroid(k, a) - clo[a]) * scale), 0), B - 1);
+                grow(blo[b], bhi[b], k);
+                bc[b]++;
+            }
+            float ra[B];
+            int rc[B];
+            float alo[3] = {INFINITY, INFINITY, INFINITY}, ahi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            int cnt = 0;
+            for (int b = B - 1; b > 0; b--) {
+                for (int k = 0; k < 3; k++) { alo[k] = std::min(alo[k], blo[b][k]); ahi[k] = std::max(ahi[k], bhi[b][k]); }
+                cnt += bc[b];
+                ra[b] = area(alo, ahi);
+                rc[b] = cnt;
+            }
+            for (int k = 0; k < 3; k++) { alo[k] = INFINITY; ahi[k] = -INFINITY; }
+            cnt = 0;
+            for (int b = 0; b < B - 1; b++) {
+                for (int k = 0; k < 3; k++) { alo[k] = std::min(alo[k], blo[b][k]); ahi[k] = std::max(ahi[k], bhi[b][k]); }
+                cnt += bc[b];
+                if (cnt == 0 || rc[b + 1] == 0) continue;
+                const float cost = area(alo, ahi) * cnt + ra[b + 1] * rc[b + 1];
+                if (cost < best) { best = cost; best_axis = a; best_split = b; }
+            }
+        }
+        int mid = first + count / 2;
+        if (best_axis >= 0) {
+            const float ext = chi[best_axis] - clo[best_axis], scale = B / ext, cmin = clo[best_axis];
+            const int a = best_axis, split = best_split;
+            int* b0 = order.data() + first;
+            int* m = std::partition(b0, b0 + count, [&](int o) {
+                return std::min(std::max((int)((centroid(c[o], a) - cmin) * scale), 0), B - 1) <= split;
+            });
+            const int mm = (int)(m - order.data());
+            if (mm != first && mm != first + count) mid = mm;
+        }
+        const int l = build(first, mid - first);
+        const int r = build(mid, first + count - mid);
+        TopNode& n = nodes[self];
+        for (int k = 0; k < 3; k++) { n.lo[k] = lo[k]; n.hi[k] = hi[k]; }
+        n.left = l;
+        n.right = r;
+        return self;
+    }
+};
+
 struct Scratch {  // frees everything it allocated when it goes out of scope
     std::vector<void*> ptrs;
     ~Scratch() {
@@ -435,7 +562,7 @@ struct Scratch {  // frees everything it allocated when it goes out of scope
     } while (0)
 
 int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_nodes, int n_ref_nodes, int max_leaf,
-                          DeviceWideBvh* out, cudaStream_t s, std::string* err) {
+                          bool top_sah, DeviceWideBvh* out, cudaStream_t s, std::string* err) {
     max_leaf = std::max(1, std::min(4, max_leaf));
     *out = DeviceWideBvh();
     Scratch tmp;
@@ -582,30 +709,89 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
         out->depth = 1;
     } else {
         const int n_int = n_rest - 1;
+        const int cluster_cap = 65536;  // > 2 * 8192 cluster roots plus stragglers
+        const int top_cap = cluster_cap;
         int *left, *right, *parent_int, *parent_leaf, *first, *last, *visits;
         float4 *ilo, *ihi;
-        BCU(tmp.get(&left, n_int));
-        BCU(tmp.get(&right, n_int));
+        BCU(tmp.get(&left, n_int + top_cap));
+        BCU(tmp.get(&right, n_int + top_cap));
         BCU(tmp.get(&parent_int, n_int));
         BCU(tmp.get(&parent_leaf, n_rest));
-        BCU(tmp.get(&first, n_int));
-        BCU(tmp.get(&last, n_int));
+        BCU(tmp.get(&first, n_int + top_cap));
+        BCU(tmp.get(&last, n_int + top_cap));
         BCU(tmp.get(&visits, n_int));
-        BCU(tmp.get(&ilo, n_int));
-        BCU(tmp.get(&ihi, n_int));
+        BCU(tmp.get(&ilo, n_int + top_cap));
+        BCU(tmp.get(&ihi, n_int + top_cap));
         BCU(cudaMemsetAsync(visits, 0, (size_t)n_int * 4, s));
         k_hierarchy<<<grid(n_int), kB, 0, s>>>(keys, n_rest, left, right, parent_int, parent_leaf, first, last);
         k_fit<<<grid(n_rest), kB, 0, s>>>(n_rest, sorted, olo, ohi, parent_leaf, parent_int, left, right, ilo, ihi, visits);
         tv.left = left; tv.right = right; tv.first = first; tv.last = last; tv.ilo = ilo; tv.ihi = ihi;
 
+        // SAH over clusters for the upper levels (HLBVH-style hybrid): cut the LBVH into subtrees of
+        // at most cmax primitives, build a binned-SAH tree over their boxes on the host (a few
+        // thousand boxes), and splice it in as extra internal nodes [n_int, n_int + n_top) above them
+        int root_ref = 0;
+        const int cmax = std::max(2 * max_leaf, n_rest / 8192);
+        if (top_sah && n_rest > 4 * cmax) {
+            BCU(cudaStreamSynchronize(s));
+            std::vector<Cluster> cl(cluster_cap);
+            Cluster* d_cl;
+            int* d_ncl;
+            BCU(tmp.get(&d_cl, cluster_cap));
+            BCU(tmp.get(&d_ncl, 1));
+            BCU(cudaMemsetAsync(d_ncl, 0, 4, s));
+            k_clusters<<<grid(n_int + n_rest), kB, 0, s>>>(n_rest, cmax, first, last, parent_int, parent_leaf, sorted, olo,
+                                                           ohi, ilo, ihi, d_cl, cluster_cap, d_ncl);
+            int n_cl = 0;
+            BCU(cudaMemcpyAsync(&n_cl, d_ncl, 4, cudaMemcpyDeviceToHost, s));
+            BCU(cudaStreamSynchronize(s));
+            if (n_cl > 1 && n_cl <= cluster_cap) {
+                cl.resize(n_cl);
+                BCU(cudaMemcpy(cl.data(), d_cl, sizeof(Cluster) * n_cl, cudaMemcpyDeviceToHost));
+                // device-side append order is arbitrary: sort by node reference so the tree is reproducible
+                std::sort(cl.begin(), cl.end(), [](const Cluster& a, const Cluster& b) {
+                    int ra, rb;
+                    memcpy(&ra, &a.lo.w, 4);
+                    memcpy(&rb, &b.lo.w, 4);
+                    return ra < rb;
+                });
+                TopSah sah(cl);
+                sah.build(0, n_cl);
+                const int n_top = (int)sah.nodes.size();  // = n_cl - 1 <= top_cap
+                std::vector<int> hl(n_top), hr(n_top), hf(n_top, 0), hla(n_top, 0x3fffffff);
+                std::vector<float4> hlo(n_top), hhi(n_top);
+                auto conv = [&](int c) {
+                    if (c >= 0) return n_int + c;
+                    int ref;
+                    memcpy(&ref, &cl[~c].lo.w, 4);
+                    return ref;
+                };
+                for (int i = 0; i < n_top; i++) {
+                    const TopNode& t = sah.nodes[i];
+                    hl[i] = conv(t.left);
+                    hr[i] = conv(t.right);
+                    hlo[i] = make_float4(t.lo[0], t.lo[1], t.lo[2], 0.f);
+                    hhi[i] = make_float4(t.hi[0], t.hi[1], t.hi[2], 0.f);
+                }
+                BCU(cudaMemcpyAsync(left + n_int, hl.data(), 4 * (size_t)n_top, cudaMemcpyHostToDevice, s));
+                BCU(cudaMemcpyAsync(right + n_int, hr.data(), 4 * (size_t)n_top, cudaMemcpyHostToDevice, s));
+                BCU(cudaMemcpyAsync(first + n_int, hf.data(), 4 * (size_t)n_top, cudaMemcpyHostToDevice, s));
+                BCU(cudaMemcpyAsync(last + n_int, hla.data(), 4 * (size_t)n_top, cudaMemcpyHostToDevice, s));
+                BCU(cudaMemcpyAsync(ilo + n_int, hlo.data(), 16 * (size_t)n_top, cudaMemcpyHostToDevice, s));
+                BCU(cudaMemcpyAsync(ihi + n_int, hhi.data(), 16 * (size_t)n_top, cudaMemcpyHostToDevice, s));
+                BCU(cudaStreamSynchronize(s));  // the host vectors go out of scope
+                root_ref = n_int;
+            }
+        }
+
         float4* wide_tmp;  // a wide node consumes at least one internal node
         Task *fr_a, *fr_b;
         int* d_cnt;  // [0] next-level tasks, [1] wide nodes allocated, [2] depth
-        BCU(tmp.get(&wide_tmp, (size_t)n_int * 8));
-        BCU(tmp.get(&fr_a, n_int));
-        BCU(tmp.get(&fr_b, n_int));
+        BCU(tmp.get(&wide_tmp, (size_t)(n_int + top_cap) * 8));
+        BCU(tmp.get(&fr_a, n_int + top_cap));
+        BCU(tmp.get(&fr_b, n_int + top_cap));
         BCU(tmp.get(&d_cnt, 4));
-        const Task root_task = {0, 0, 1};
+        const Task root_task = {root_ref, 0, 1};
         const int init_cnt[4] = {0, 1, 0, 0};
         BCU(cudaMemcpyAsync(fr_a, &root_task, sizeof(Task), cudaMemcpyHostToDevice, s));
         BCU(cudaMemcpyAsync(d_cnt, init_cnt, sizeof(init_cnt), cudaMemcpyHostToDevice, s));
@@ -627,8 +813,8 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
         out->depth = h_cnt[2];
         BCU(cudaMalloc(&out->d_nodes, (size_t)out->n_nodes * 128));
         BCU(cudaMemcpyAsync(out->d_nodes, wide_tmp, (size_t)out->n_nodes * 128, cudaMemcpyDeviceToDevice, s));
-        BCU(cudaMemcpyAsync(d_root, ilo, 16, cudaMemcpyDeviceToDevice, s));
-        BCU(cudaMemcpyAsync(d_root + 1, ihi, 16, cudaMemcpyDeviceToDevice, s));
+        BCU(cudaMemcpyAsync(d_root, ilo + root_ref, 16, cudaMemcpyDeviceToDevice, s));
+        BCU(cudaMemcpyAsync(d_root + 1, ihi + root_ref, 16, cudaMemcpyDeviceToDevice, s));
     }
     float4 h_root[2];
     BCU(cudaMemcpyAsync(h_root, d_root, 32, cudaMemcpyDeviceToHost, s));

@@ -30,8 +30,9 @@ struct DeviceWideBvh {
 // d_objects: n_objects x 112 B (7 float4).  d_ref_nodes: the reference node array (3 float4 per
 // node) whose leaves define each object's reference leaf box, or nullptr: then the box is derived
 // from the vertices with the reference builder's rule (reference src/bvh.cpp:12-30).
-// max_leaf in [1, 4].  Returns 0, or -1 with *err set.
+// max_leaf in [1, 4].  top_sah: rebuild the upper levels with a binned-SAH pass over LBVH clusters
+// (HLBVH-style hybrid; a few thousand boxes, done on the host).  Returns 0, or -1 with *err set.
 int build_wide_bvh_device(const float4* d_objects, int n_objects, const float4* d_ref_nodes, int n_ref_nodes,
-                          int max_leaf, DeviceWideBvh* out, cudaStream_t s, std::string* err);
+                          int max_leaf, bool top_sah, DeviceWideBvh* out, cudaStream_t s, std::string* err);
 
 }  // namespace trt
