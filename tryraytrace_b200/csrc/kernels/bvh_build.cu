@@ -326,8 +326,25 @@ struct TreeView {
     int max_leaf;
 };
 
+__device__ __forceinline__ void child_box(const TreeView& t, int c, float4* l, float4* h);
+
+// A subtree of at most max_leaf primitives becomes ONE leaf when that is cheaper than opening it
+// by the host builder's SAH rule (host/wide_bvh.cpp: a triangle test costs 2.5 child-box tests):
+//     2.5 * n  <=  2 + 2.5 * (A_l * n_l + A_r * n_r) / A
 __device__ __forceinline__ bool leaf_like(const TreeView& t, int c) {
-    return c < 0 || (t.last[c] - t.first[c] + 1) <= t.max_leaf;
+    if (c < 0) return true;
+    const int n = t.last[c] - t.first[c] + 1;
+    if (n > t.max_leaf) return false;
+    const float a = box_area(t.ilo[c], t.ihi[c]);
+    float split = 0.f;
+    const int kid[2] = {t.left[c], t.right[c]};
+    for (int k = 0; k < 2; k++) {
+        float4 l, h;
+        child_box(t, kid[k], &l, &h);
+        const int nk = kid[k] < 0 ? 1 : t.last[kid[k]] - t.first[kid[k]] + 1;
+        split += box_area(l, h) * (float)nk;
+    }
+    return 2.5f * (float)n <= 2.f + 2.5f * split / fmaxf(a, 1e-30f);
 }
 __device__ __forceinline__ void child_box(const TreeView& t, int c, float4* l, float4* h) {
     if (c < 0) {
