@@ -45,7 +45,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(TRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kFrameChunk = 64;       // frames per wavefront job (bounds the column-vector table)
+int kFrameChunk = 64;                 // frames per wavefront job (bounds the column-vector table); TRT_FRAME_CHUNK overrides
 constexpr int kBatchIterations = 16;  // iterations issued between completion polls
 constexpr int kWideStackEntries = 128;  // kernels/traverse_fast.cuh kSpillEntries
 constexpr int kAutoDeviceBuildAbove = 1 << 18;  // TRT_BUILD_AUTO: objects above which the device builder is used
@@ -87,6 +87,7 @@ struct trt_ctx {
     void* pool_mem = nullptr;
     PoolView pool{};
     int* d_free = nullptr;
+    int* d_compact = nullptr;  // drain-phase compaction lists (kernels/wavefront.cu k_compact_*)
     // scratch pool of the parity entry points (FAST mode runs the production kernels over it)
     int scratch_cap = 0;
     void* scratch_mem = nullptr;
@@ -237,9 +238,12 @@ int ensure_pool(trt_ctx* c, int cap) {
     cap = std::max(256, (cap + 255) & ~255);
     if (c->pool_cap == cap) return 0;
     cudaFree(c->pool_mem);
+    cudaFree(c->d_compact);
     c->pool_mem = nullptr;
+    c->d_compact = nullptr;
     c->pool_cap = 0;
     if (int rc = alloc_pool(cap, true, &c->pool_mem, &c->pool, &c->d_free)) return rc;
+    CU(cudaMalloc(&c->d_compact, ((size_t)cap + 1024) * sizeof(int)));
     c->pool_cap = cap;
     return 0;
 }
@@ -274,10 +278,12 @@ LaunchDims launch_dims(const trt_ctx* c) {
     const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
     d.smem_nodes = fit;
     if (const char* e = getenv("TRT_SMEM_NODES")) d.smem_nodes = std::max(0, std::min(fit, atoi(e)));
-    d.refill_below = 25;
+    d.refill_below = 32;
+    d.compact_quarters = 3;
+    if (const char* e = getenv("TRT_COMPACT_QUARTERS")) d.compact_quarters = std::max(1, std::min(3, atoi(e)));
     if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
-    d.closest_phases = Phases{2, 16, 12};
-    d.shadow_phases = Phases{2, 16, 12};
+    d.closest_phases = Phases{2, 12, 8};
+    d.shadow_phases = Phases{2, 12, 8};
     if (const char* e = getenv("TRT_PHASES")) {  // "iters,node_min,tri_min[,iters,node_min,tri_min]" closest[,shadow]
         int v[6] = {1, 33, 33, 1, 33, 33};
         const int n = sscanf(e, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
@@ -362,7 +368,10 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_pool(c, pool_paths)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
+    if (const char* e = getenv("TRT_FRAME_CHUNK")) kFrameChunk = std::max(1, std::min(1024, atoi(e)));
     c->marks_used = 0;
+    bool compact = true;
+    if (const char* e = getenv("TRT_COMPACT")) compact = atoi(e) != 0;
     const LaunchDims dims = launch_dims(c);
     const int kpi = wf_kernels_per_iteration(o.traversal);
     CU(cudaEventRecord(c->ev_begin, c->stream));
@@ -377,6 +386,9 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         wf_begin_job(c->d_ctl, pixels * nf, c->pool_cap, c->stream);
         c->launches += 3;
         // Issue batches of iterations, staying one batch ahead of the completion poll.
+        // the compaction kernels ride along once the job can reach its drain phase within the batches
+        // in flight (the poll is up to two batches old; an iteration starts about capacity / 6 samples)
+        bool near_drain = pixels * nf <= 8ull * (unsigned long long)c->pool_cap;
         auto issue = [&](int slot) -> int {
             for (int i = 0; i < kBatchIterations; i++) {
                 cudaEvent_t* marks = nullptr;
@@ -390,9 +402,9 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
                     c->marks_used += 5;
                 }
                 wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, c->top, job, o.traversal, o.count_rays != 0, dims,
-                             c->stream, marks);
+                             c->stream, marks, near_drain && compact ? c->d_compact : nullptr);
             }
-            c->launches += (unsigned long long)kBatchIterations * kpi;
+            c->launches += (unsigned long long)kBatchIterations * (kpi + (near_drain && compact ? 3 : 0));
             CU(cudaMemcpyAsync(&c->h_ctl[slot], c->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaEventRecord(c->ev_poll[slot], c->stream));
             return 0;
@@ -409,6 +421,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
             CU(cudaEventSynchronize(c->ev_poll[b & 1]));
             const Control& hc = c->h_ctl[b & 1];
             if (hc.alive == 0 && hc.next_sample == hc.total_samples) break;
+            if (hc.total_samples - hc.next_sample <= 8ull * (unsigned long long)c->pool_cap) near_drain = true;
             if (++b > max_batches) {
                 cudaStreamSynchronize(c->stream);
                 return fail(TRT_ERR_STATE, "wavefront did not drain after %llu batches (alive=%d, next=%llu of %llu)",
@@ -480,6 +493,7 @@ int trt_destroy(trt_ctx* c) {
     cudaFree(c->d_col_pows);
     cudaFree(c->d_col_vecs);
     cudaFree(c->pool_mem);
+    cudaFree(c->d_compact);
     cudaFree(c->scratch_mem);
     cudaFree(c->d_ctl);
     cudaFreeHost(c->h_ctl);

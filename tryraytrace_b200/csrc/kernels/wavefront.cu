@@ -16,6 +16,7 @@ namespace trt {
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kCompactMinCap = 32 * 1024;  // the pool is not compacted below this many slots
 
 TRT_DEV int pack_flags(int state, int depth, int mode) { return state | (depth << 8) | (mode << 16); }
 
@@ -43,7 +44,7 @@ TRT_DEV int block_append(bool want, int* counter, int* smem_scratch /* >= 2 + wa
 }
 
 // ---- prepare: single thread, advances the queue bookkeeping between iterations --------
-__global__ void k_prepare(Control* ctl) {
+__global__ void k_prepare(Control* ctl, int compact_quarters) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int n_free = ctl->n_free;
     const unsigned long long remaining = ctl->total_samples - ctl->next_sample;
@@ -57,6 +58,14 @@ __global__ void k_prepare(Control* ctl) {
     ctl->n_free = 0;
     ctl->cursor_extend = 0;
     ctl->cursor_shadow = 0;
+    // drain phase: no sample left to start, and at most half of the visited slots still hold a path
+    const int cap = ctl->active_cap;
+    const bool go = ctl->next_sample == ctl->total_samples && cap > kCompactMinCap && (long long)ctl->alive * 4 <= (long long)cap * compact_quarters;
+    ctl->compact_go = go ? 1 : 0;
+    if (go) {
+        ctl->compact_new_cap = max(kCompactMinCap, (ctl->alive + kBlock - 1) / kBlock * kBlock);
+        ctl->compact_a = ctl->compact_b = 0;
+    }
 }
 
 __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity) {
@@ -64,6 +73,8 @@ __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity
     ctl->next_sample = 0;
     ctl->total_samples = total;
     ctl->n_free = capacity;  // every slot is free (the free list is the identity)
+    ctl->active_cap = capacity;
+    ctl->compact_go = 0;
     ctl->alive = capacity;   // prepare subtracts n_free and adds n_regen
     ctl->n_shadow = 0;
     ctl->n_regen = 0;
@@ -82,6 +93,61 @@ __global__ void k_reset_cursors(Control* ctl) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->cursor_extend = 0;
     ctl->cursor_shadow = 0;
+    ctl->active_cap = 0x7fffffff;  // scratch pools of the parity entry points are visited whole
+}
+
+// ---- drain-phase compaction -----------------------------------------------------------------
+// When a job has handed out its last sample the pool thins out: paths end, nothing refills their
+// slots, and every kernel keeps paying for the dead ones (a 32-slot chunk with three live rays
+// costs the traversal kernels a full top phase).  Each time the live paths drop to 3/4 of the visited
+// slots (LaunchDims::compact_quarters), the live
+// slots beyond the new bound are moved into dead slots below it and active_cap shrinks, so the
+// kernels of the remaining iterations visit a dense prefix of the pool.
+// scan: A = live slots in [new_cap, active_cap), B = dead slots in [0, new_cap)   (|B| >= |A|)
+__global__ void __launch_bounds__(kBlock) k_compact_scan(PoolView pool, Control* ctl, int* list_a, int* list_b) {
+    if (!ctl->compact_go) return;
+    const int cap = ctl->active_cap, new_cap = ctl->compact_new_cap;
+    const unsigned lane = threadIdx.x & 31u;
+    for (int base = blockIdx.x * blockDim.x; base < cap; base += gridDim.x * blockDim.x) {
+        const int slot = base + threadIdx.x;
+        const bool live = slot < cap && (f2i(pool.ray_d[slot].w) & 0xff) != SLOT_DEAD;
+        const bool to_a = live && slot >= new_cap, to_b = !live && slot < new_cap;
+        const unsigned ma = __ballot_sync(0xffffffffu, to_a), mb = __ballot_sync(0xffffffffu, to_b);
+        int ba = 0, bb = 0;
+        if (lane == 0) {
+            if (ma) ba = atomicAdd(&ctl->compact_a, __popc(ma));
+            if (mb) bb = atomicAdd(&ctl->compact_b, __popc(mb));
+        }
+        ba = __shfl_sync(0xffffffffu, ba, 0);
+        bb = __shfl_sync(0xffffffffu, bb, 0);
+        if (to_a) list_a[ba + __popc(ma & ((1u << lane) - 1u))] = slot;
+        if (to_b) list_b[bb + __popc(mb & ((1u << lane) - 1u))] = slot;
+    }
+}
+
+// move: slot A[i] -> slot B[i], every array of the pool
+__global__ void __launch_bounds__(kBlock) k_compact_move(PoolView pool, const Control* __restrict__ ctl,
+                                                         const int* __restrict__ list_a, const int* __restrict__ list_b) {
+    if (!ctl->compact_go) return;
+    const int n = ctl->compact_a;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int src = list_a[i], dst = list_b[i];
+        pool.ray_o[dst] = pool.ray_o[src];
+        pool.ray_d[dst] = pool.ray_d[src];
+        pool.thr[dst] = pool.thr[src];
+        pool.rad[dst] = pool.rad[src];
+        pool.pend[dst] = pool.pend[src];
+        pool.sh_d[dst] = pool.sh_d[src];
+        pool.rng_a[dst] = pool.rng_a[src];
+        pool.rng_b[dst] = pool.rng_b[src];
+        pool.hit[dst] = pool.hit[src];
+    }
+}
+
+__global__ void k_compact_commit(Control* ctl) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || !ctl->compact_go) return;
+    ctl->active_cap = ctl->compact_new_cap;
+    ctl->compact_go = 0;
 }
 
 __global__ void k_init_pool(PoolView pool, int* free_list) {
@@ -164,7 +230,8 @@ TRT_DEV void warp_add(unsigned long long* counter, unsigned v) {
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev sc, Control* ctl) {
     unsigned nodes = 0, tris = 0, rays = 0;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pool.capacity; slot += gridDim.x * blockDim.x) {
+    const int cap = min(pool.capacity, ctl->active_cap);
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < cap; slot += gridDim.x * blockDim.x) {
         const float4 d4 = pool.ray_d[slot];
         if ((f2i(d4.w) & 0xff) != SLOT_ACTIVE) continue;
         const float4 o4 = pool.ray_o[slot];
@@ -197,7 +264,9 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
                                                   SceneDev sc, JobParams job) {
     __shared__ int scratch[2 + kBlock / 32];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of kBlock
-    const bool eager = ctl->alive * 2 > pool.capacity;
+    const int cap = ctl->active_cap;                         // ... and so is the compacted bound
+    if (blockIdx.x * blockDim.x >= cap) return;              // whole block beyond the visited prefix
+    const bool eager = ctl->alive * 2 > cap;
     const float4 d4 = pool.ray_d[slot];
     float4 thr4, rad4, pend4, o4;
     float2 hit;
@@ -285,7 +354,8 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_shadow_ref(PoolView pool, SceneDev sc, Control* ctl) {
     unsigned nodes = 0, tris = 0, rays = 0;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < pool.capacity; slot += gridDim.x * blockDim.x) {
+    const int cap = min(pool.capacity, ctl->active_cap);
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < cap; slot += gridDim.x * blockDim.x) {
         const float4 d4 = pool.sh_d[slot];
         if (f2i(d4.w) != 1) continue;
         const float4 o4 = pool.ray_o[slot];
@@ -425,6 +495,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
     const uint32_t stk_ttop = stk_base + (S - 1) * E;
     uint2 spill[kSpillEntries];
+    const int slot_limit = min(pool.capacity, ctl->active_cap);
     Feeder fd;
     feeder_init(fd);
     ClosestRay st;
@@ -442,7 +513,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         unsigned act = __ballot_sync(0xffffffffu, has);
         // 1. top phase on fresh chunks while the queue has room for a whole chunk
         while (qn <= kQueueLow && !feeder_exhausted(fd)) {
-            feeder_advance(fd, stage, bars, pool.ray_o, pool.ray_d, &ctl->cursor_extend, pool.capacity, lane,
+            feeder_advance(fd, stage, bars, pool.ray_o, pool.ray_d, &ctl->cursor_extend, slot_limit, lane,
                            act == 0 && qn == 0);
             if (!fd.fresh) break;  // the next chunk has not landed: traverse meanwhile
             const float4* buf = stage + fd.cur_buf * (2 * kChunk);
@@ -546,6 +617,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
     const uint32_t stk_ttop = stk_base + (S - 1) * E;
     uint32_t spill[kSpillEntries];
+    const int slot_limit = min(pool.capacity, ctl->active_cap);
     Feeder fd;
     feeder_init(fd);
     ShadowRay st;
@@ -562,7 +634,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
         while (qn <= kQueueLow && !feeder_exhausted(fd)) {
-            feeder_advance(fd, stage, bars, pool.ray_o, pool.sh_d, &ctl->cursor_shadow, pool.capacity, lane,
+            feeder_advance(fd, stage, bars, pool.ray_o, pool.sh_d, &ctl->cursor_shadow, slot_limit, lane,
                            act == 0 && qn == 0);
             if (!fd.fresh) break;
             const float4* buf = stage + fd.cur_buf * (2 * kChunk);
@@ -872,12 +944,20 @@ int wf_kernels_per_iteration(int) { return 5; }
 
 template <int MODE, bool COUNT>
 static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
-                           const JobParams& job, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks) {
+                           const JobParams& job, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks,
+                           int* compact_lists) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
     auto mark = [&](int i) { if (marks) cudaEventRecord(marks[i], s); };
     mark(0);
-    k_prepare<<<1, 32, 0, s>>>(ctl);
+    k_prepare<<<1, 32, 0, s>>>(ctl, dims.compact_quarters);
+    if (compact_lists) {  // the host launches these only once the job is close to its drain phase
+        int* list_a = compact_lists;
+        int* list_b = compact_lists + pool.capacity / 2 + 512;
+        k_compact_scan<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b);
+        k_compact_move<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b);
+        k_compact_commit<<<1, 32, 0, s>>>(ctl);
+    }
     // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
     // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up
     const int regen_blocks = min(full, max(persistent, full / 4));
@@ -895,13 +975,13 @@ static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, c
 
 void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
                   const JobParams& job, int traversal, bool count, const LaunchDims& dims, cudaStream_t s,
-                  cudaEvent_t* marks) {
+                  cudaEvent_t* marks, int* compact_lists) {
     if (traversal == TRT_TRAVERSE_REF) {
-        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, s, marks);
-        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, s, marks);
+        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
+        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
     } else {
-        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, s, marks);
-        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, s, marks);
+        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
+        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
     }
 }
 

@@ -44,6 +44,9 @@ struct Control {
     int alive;         // slots that hold a live path
     int cursor_extend, cursor_shadow, cursor_replay;
     int n_replay;
+    // drain-phase compaction (wavefront.cu k_compact_*): slots [0, active_cap) are the only ones any
+    // kernel visits; it shrinks when the job has no samples left and the live paths have halved
+    int active_cap, compact_go, compact_new_cap, compact_a, compact_b;
     // counters (see trt_counters)
     unsigned long long cnt_samples, cnt_closest, cnt_shadow, cnt_replays, cnt_iterations;
     unsigned long long cnt_nodes, cnt_tris;                // all queries (COUNT builds only)
@@ -77,6 +80,7 @@ struct LaunchDims {
     int fast_threads;   // threads of the persistent traversal CTAs (one CTA per SM): 512, 768 or 1024
     int smem_nodes;     // wide nodes staged into shared memory per CTA (top of the tree)
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
+    int compact_quarters;  // drain phase: compact when live paths <= this many quarters of the visited slots (1..3)
     Phases closest_phases, shadow_phases;
 };
 
@@ -96,7 +100,7 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
 // iteration: [prepare+regenerate] m1 [extend] m2 [shade] m3 [shadow] m4  (m0 first).
 void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
                   const JobParams& job, int traversal, bool count, const LaunchDims& dims, cudaStream_t s,
-                  cudaEvent_t* marks = nullptr);
+                  cudaEvent_t* marks = nullptr, int* compact_lists = nullptr);
 // one-time opt-in to large dynamic shared memory for the persistent kernels
 int wf_configure();
 int wf_kernels_per_iteration(int traversal);
