@@ -98,3 +98,14 @@ def test_scene_of_a_few_triangles_has_no_root_level_list(trt, ref, ctx, assets):
     cam, w, h = trt.config_camera(1, 160, 120)
     radiance_gate(trt, ref, ctx, sc, cam, w, h, 4, "9-triangle scene")
     assert ctx.scene_info()["n_top_prims"] == 0
+
+
+def test_open_scene_with_short_paths_drains_correctly(trt, ref, ctx, assets):
+    """C5 at a 2 x 2 grid: most paths leave the scene after a bounce or two, so the job hands out its
+    last samples while the pool is already thin -- the drain-phase compaction must not start in the
+    iteration that still regenerates (regression: paths were moved into slots about to be refilled)."""
+    sc = trt.HostScene.from_config(5, assets, grid=2)
+    cam, w, h = trt.config_camera(5, 640, 360)
+    for pool in (1 << 16, 1 << 18):
+        a = radiance_gate(trt, ref, ctx, sc, cam, w, h, 6, f"C5 2x2 pool {pool}", pool_paths=pool)
+        assert float(a.sum()) > 0

@@ -60,7 +60,8 @@ __global__ void k_prepare(Control* ctl, int compact_quarters) {
     ctl->cursor_shadow = 0;
     // drain phase: no sample left to start, and at most half of the visited slots still hold a path
     const int cap = ctl->active_cap;
-    const bool go = ctl->next_sample == ctl->total_samples && cap > kCompactMinCap && (long long)ctl->alive * 4 <= (long long)cap * compact_quarters;
+    // (n_regen == 0: the slots this iteration's regenerate is about to fill are still marked dead)
+    const bool go = n_regen == 0 && ctl->next_sample == ctl->total_samples && cap > kCompactMinCap && (long long)ctl->alive * 4 <= (long long)cap * compact_quarters;
     ctl->compact_go = go ? 1 : 0;
     if (go) {
         ctl->compact_new_cap = max(kCompactMinCap, (ctl->alive + kBlock - 1) / kBlock * kBlock);
