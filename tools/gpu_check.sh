@@ -1,4 +1,5 @@
 #!/bin/bash
+# full GPU parity suite, then C2 timings at 16 / 64 spp and C1 with the drain compaction off and on
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_state.log 2>&1
 echo "pytest exit: $?"; grep -E "passed|failed|Error|assert" gpurun_out/pytest_gpu_state.log | tail -5

@@ -36,10 +36,10 @@
 //
 // Execution model (kernels in wavefront.cu).  One persistent CTA per SM.  Two levels:
 //   * TOP PHASE.  A warp takes a chunk of 32 consecutive pool slots, one ray per lane, and tests
-//     the root-level list (the oversized primitives the builder lifted out of the tree, <= 12,
-//     in the constant bank) brute force and fully converged, plus the tree's bounding box.  In
-//     the benchmark scenes ~3/4 of all rays are decided right there (they only ever see the
-//     room's walls) at 100% lane utilisation and without touching a stack.
+//     the root-level list (the oversized primitives and the light sources the builder lifted out
+//     of the tree, <= 12, in the constant bank) brute force and fully converged, plus the tree's
+//     bounding box.  In the benchmark scenes 60-80% of all rays are decided right there (they only
+//     ever see the room's walls) at 100% lane utilisation and without touching a stack.
 //   * TREE PHASE.  Rays that enter the tree are compacted (__ballot_sync/__popc) into a per-warp
 //     queue in shared memory, carrying the d_min / id found so far; idle traversal lanes refill
 //     from that queue.

@@ -77,9 +77,7 @@ __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity
     ctl->active_cap = capacity;
     ctl->compact_go = 0;
     ctl->alive = capacity;   // prepare subtracts n_free and adds n_regen
-    ctl->n_shadow = 0;
     ctl->n_regen = 0;
-    ctl->n_replay = 0;
 }
 
 __global__ void k_reset_counters(Control* ctl) {

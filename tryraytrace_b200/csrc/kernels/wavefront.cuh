@@ -40,10 +40,8 @@ struct Control {
     int n_free;        // free-list entries appended by the last shade pass
     int n_regen;       // slots to regenerate this iteration
     unsigned long long regen_base;  // first sample index for this iteration's regeneration
-    int n_shadow;      // unused (shadow rays are in place)
     int alive;         // slots that hold a live path
-    int cursor_extend, cursor_shadow, cursor_replay;
-    int n_replay;
+    int cursor_extend, cursor_shadow;  // next chunk of the persistent traversal kernels
     // drain-phase compaction (wavefront.cu k_compact_*): slots [0, active_cap) are the only ones any
     // kernel visits; it shrinks when the job has no samples left and the live paths have halved
     int active_cap, compact_go, compact_new_cap, compact_a, compact_b;
