@@ -210,10 +210,11 @@ __global__ void __launch_bounds__(kBlock) k_regen(PoolView pool, const int* __re
         const int y = job.rc.height - 1 - row;          // i = (h-1-y)*w + x  (reference :322)
         Xorwow rng = sample_rng(job, f, row, col);
         const Ray r = primary_ray(job.cam, col, y, job.rc.width, job.rc.height, rng);
-        pool.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, 0.f);
+        // a fresh path has throughput 1 and no radiance: neither array is written (scattered 16-byte
+        // stores cost a read-modify-write of the 32-byte sector); the pixel index rides in ray_o.w,
+        // which only carries a shadow-ray length from depth 1 on, until shade moves it to thr.w
+        pool.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, i2f(pix));
         pool.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
-        pool.thr[slot] = make_float4(1.f, 1.f, 1.f, i2f(pix));
-        pool.rad[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
         pool.rng_a[slot] = make_uint4(rng.v0, rng.v1, rng.v2, rng.v3);
         pool.rng_b[slot] = make_uint2(rng.v4, rng.d);
     }
@@ -285,10 +286,11 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
         }
         PathVertexIO io;
         io.shadow = false;
-        const int pix = f2i(thr4.w);
-        io.thr = f3(thr4.x, thr4.y, thr4.z);
-        io.rad = f3(rad4.x, rad4.y, rad4.z);
         io.depth = (flags >> 8) & 0xff;
+        const bool fresh = io.depth == 0;  // regenerate leaves thr / rad unwritten and the pixel in ray_o.w
+        const int pix = fresh ? f2i(o4.w) : f2i(thr4.w);
+        io.thr = fresh ? f3(1.f, 1.f, 1.f) : f3(thr4.x, thr4.y, thr4.z);
+        io.rad = fresh ? f3(0.f, 0.f, 0.f) : f3(rad4.x, rad4.y, rad4.z);
         // next-event estimate of the previous vertex; the shadow kernel zeroed it if occluded
         if (io.depth > 0) io.rad = v_add(io.rad, f3(pend4.x, pend4.y, pend4.z));
         if (state == SLOT_ACTIVE) {
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
                     pool.ray_o[slot] = make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, io.shadow ? io.shadow_max_dist : 0.f);
                     pool.ray_d[slot] = make_float4(io.ray.d.x, io.ray.d.y, io.ray.d.z,
                                                    i2f(pack_flags(ns, depth, io.prev_mode)));
-                    pool.thr[slot] = make_float4(io.thr.x, io.thr.y, io.thr.z, thr4.w);
+                    pool.thr[slot] = make_float4(io.thr.x, io.thr.y, io.thr.z, i2f(pix));
                     pool.rad[slot] = make_float4(io.rad.x, io.rad.y, io.rad.z, 0.f);
                     pool.rng_a[slot] = make_uint4(io.rng.v0, io.rng.v1, io.rng.v2, io.rng.v3);
                     pool.rng_b[slot] = make_uint2(io.rng.v4, io.rng.d);
