@@ -63,7 +63,9 @@ struct WideCounts {
 };
 
 constexpr int kWideEmptyRef = 0x7fffffff;
-constexpr int kSmemNodeStride = 144;  // bytes between staged nodes in shared memory (128 + 16 pad)
+constexpr int kSmemNodeStride = 112;  // bytes between staged nodes in shared memory: the 7 used float4 of a node
+                                      // (the pad word is not staged); 112 = 28 banks, so consecutive nodes start in
+                                      // 8 different 16-byte bank groups
 constexpr int kSpillEntries = 128;  // logical node stack bound: 3 * wide depth + 1 (checked at upload)
 constexpr float kCullSlack = 1.0005f;
 constexpr int kTriIdMask = 0x3fffffff;
@@ -263,8 +265,8 @@ struct NodeData {
 
 // `near_off` packs the byte offsets of the near-plane vectors inside the 128-byte node:
 // x: 0 or 16, y: 32 or 48, z: 64 or 80; the far plane is the other one of each pair (^16).
-// The first k_smem nodes are staged in shared memory 144 bytes apart (the 16-byte plane vector a
-// lane reads then falls into bank group (node + k) mod 8, so lanes reading the same k of
+// The first k_smem nodes are staged in shared memory 112 bytes apart (the 16-byte plane vector a
+// lane reads then falls into bank group (k - node) mod 8, so lanes reading the same k of
 // different nodes spread over the banks), the rest sit in global memory 128 bytes apart.  Both
 // are read through ONE generic-address code path: a warp whose lanes are split between the two
 // spaces issues the seven loads once, not twice.

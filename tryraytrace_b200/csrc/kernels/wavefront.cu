@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_ref(PoolView pool, SceneDev s
 //      step per lane).
 constexpr int kChunk = 32;
 constexpr int kStageBytesPerWarp = 2 * 2 * kChunk * 16;  // 2 buffers x (o + d) x 32 x float4
-constexpr int kQueueCap = 64;                             // entries; the top phase runs while <= kQueueLow are queued
+constexpr int kQueueCap = 48;                             // entries; the top phase runs while <= kQueueLow are queued
 constexpr int kQueueLow = kQueueCap - kChunk;
 constexpr int kQueueBytesClosest = kQueueCap * (16 + 16 + 4);
 constexpr int kQueueBytesShadow = kQueueCap * (16 + 16);
@@ -479,7 +479,8 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
-        reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
+        if ((i & 7) != 7)  // the eighth float4 of a node is padding
+            reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
     if (lane == 0) {
         mbar_init(&s_bars[warp * 2], 1);
         mbar_init(&s_bars[warp * 2 + 1], 1);
@@ -602,7 +603,8 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
-        reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
+        if ((i & 7) != 7)  // the eighth float4 of a node is padding
+            reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
     if (lane == 0) {
         mbar_init(&s_bars[warp * 2], 1);
         mbar_init(&s_bars[warp * 2 + 1], 1);
