@@ -57,6 +57,8 @@ struct trt_ctx {
     int sms = 148;
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // created by trt_create
+    cudaStream_t side_stream = nullptr; // overlapped regeneration (kernels/wavefront.cuh IterStreams)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
     float last_ms = 0.f;
     unsigned long long launches = 0;
@@ -97,7 +99,7 @@ struct trt_ctx {
     Control* h_ctl = nullptr;  // pinned, 2 entries
 
     // per-kernel timing (trt_opts.time_kernels)
-    std::vector<cudaEvent_t> marks;  // 5 per timed iteration
+    std::vector<cudaEvent_t> marks;  // 6 per timed iteration
     size_t marks_used = 0;
     trt_kernel_times ktimes{};
 
@@ -279,6 +281,8 @@ LaunchDims launch_dims(const trt_ctx* c) {
     d.smem_nodes = fit;
     if (const char* e = getenv("TRT_SMEM_NODES")) d.smem_nodes = std::max(0, std::min(fit, atoi(e)));
     d.refill_below = 32;
+    d.regen_block = 128;
+    if (const char* e = getenv("TRT_REGEN_BLOCK")) d.regen_block = std::max(32, std::min(256, atoi(e) / 32 * 32));
     d.compact_quarters = 3;
     if (const char* e = getenv("TRT_COMPACT_QUARTERS")) d.compact_quarters = std::max(1, std::min(3, atoi(e)));
     if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
@@ -370,6 +374,8 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
 
     if (const char* e = getenv("TRT_FRAME_CHUNK")) kFrameChunk = std::max(1, std::min(1024, atoi(e)));
     c->marks_used = 0;
+    IterStreams st{c->stream, c->side_stream, c->ev_fork, c->ev_join, true};
+    if (const char* e = getenv("TRT_OVERLAP")) st.overlap = atoi(e) != 0;
     bool compact = true;
     if (const char* e = getenv("TRT_COMPACT")) compact = atoi(e) != 0;
     const LaunchDims dims = launch_dims(c);
@@ -385,6 +391,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         wf_init_pool(c->pool, c->d_free, c->d_ctl, c->stream);
         wf_begin_job(c->d_ctl, pixels * nf, c->pool_cap, c->stream);
         c->launches += 3;
+        if (st.overlap) CU(cudaEventRecord(st.fork, c->stream));
         // Issue batches of iterations, staying one batch ahead of the completion poll.
         // the compaction kernels ride along once the job can reach its drain phase within the batches
         // in flight (the poll is up to two batches old; an iteration starts about capacity / 6 samples)
@@ -393,16 +400,16 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
             for (int i = 0; i < kBatchIterations; i++) {
                 cudaEvent_t* marks = nullptr;
                 if (o.time_kernels) {
-                    while (c->marks.size() < c->marks_used + 5) {
+                    while (c->marks.size() < c->marks_used + 6) {
                         cudaEvent_t e;
                         CU(cudaEventCreate(&e));
                         c->marks.push_back(e);
                     }
                     marks = c->marks.data() + c->marks_used;
-                    c->marks_used += 5;
+                    c->marks_used += 6;
                 }
                 wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, c->top, job, o.traversal, o.count_rays != 0, dims,
-                             c->stream, marks, near_drain && compact ? c->d_compact : nullptr);
+                             st, marks, near_drain && compact ? c->d_compact : nullptr);
             }
             c->launches += (unsigned long long)kBatchIterations * (kpi + (near_drain && compact ? 3 : 0));
             CU(cudaMemcpyAsync(&c->h_ctl[slot], c->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
@@ -471,6 +478,9 @@ int trt_create(int device, trt_ctx** out) {
         return fail(TRT_ERR_CUDA, "cannot opt in to %d bytes of shared memory per block", smem_optin);
     }
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev_begin));
     CU(cudaEventCreate(&c->ev_end));
@@ -503,6 +513,9 @@ int trt_destroy(trt_ctx* c) {
     cudaEventDestroy(c->ev_end);
     cudaEventDestroy(c->ev_poll[0]);
     cudaEventDestroy(c->ev_poll[1]);
+    cudaEventDestroy(c->ev_fork);
+    cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->side_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -829,10 +842,11 @@ int trt_kernel_times_get(trt_ctx* c, trt_kernel_times* out) {
     CU(cudaStreamSynchronize(c->stream));
     trt_kernel_times t;
     memset(&t, 0, sizeof(t));
-    for (size_t i = 0; i + 5 <= c->marks_used; i += 5) {
+    for (size_t i = 0; i + 6 <= c->marks_used; i += 6) {  // marks: [0] prepare+regenerate [1], [2] extend [3] shade [4] shadow [5]
         float ms[4];
-        for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], c->marks[i + k], c->marks[i + k + 1]));
-        t.regen_ms += ms[0];
+        CU(cudaEventElapsedTime(&ms[0], c->marks[i], c->marks[i + 1]));
+        for (int k = 1; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], c->marks[i + k + 1], c->marks[i + k + 2]));
+        t.regen_ms += ms[0];  // overlaps the previous iteration's shadow kernel unless TRT_OVERLAP=0
         t.extend_ms += ms[1];
         t.shade_ms += ms[2];
         t.shadow_ms += ms[3];

@@ -56,8 +56,8 @@ __global__ void k_prepare(Control* ctl, int compact_quarters) {
     ctl->cnt_samples += (unsigned long long)n_regen;
     ctl->cnt_iterations += 1;
     ctl->n_free = 0;
-    ctl->cursor_extend = 0;
-    ctl->cursor_shadow = 0;
+    ctl->cursor_extend = 0;  // cursor_shadow is reset by the shade kernel: with overlapped regeneration the
+                             // previous iteration's shadow kernel may still be pulling chunks
     // drain phase: no sample left to start, and at most half of the visited slots still hold a path
     const int cap = ctl->active_cap;
     // (n_regen == 0: the slots this iteration's regenerate is about to fill are still marked dead)
@@ -265,6 +265,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict
     __shared__ int scratch[2 + kBlock / 32];
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of kBlock
     const int cap = ctl->active_cap;                         // ... and so is the compacted bound
+    if (slot == 0) ctl->cursor_shadow = 0;                   // the shadow kernel of this iteration starts at chunk 0
     if (blockIdx.x * blockDim.x >= cap) return;              // whole block beyond the visited prefix
     const bool eager = ctl->alive * 2 > cap;
     const float4 d4 = pool.ray_d[slot];
@@ -945,46 +946,66 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
 
 int wf_kernels_per_iteration(int) { return 5; }
 
+// One iteration.  Side part: prepare -> [compact] -> regenerate.  Main part: extend -> shade -> shadow.
+// With st.overlap the side part of iteration i+1 runs on its own stream as soon as shade(i) is done,
+// i.e. concurrently with shadow(i): regenerate is a latency-bound stream of scattered stores
+// (about a sixth of the slots), the shadow kernel is issue bound and leaves room for one small
+// regenerate CTA per SM, so the refill disappears behind the traversal.  The two touch disjoint
+// state: regenerate writes slots that ended in shade(i) (their shadow flag is already cleared),
+// prepare leaves the shadow cursor alone.  Compaction moves slots the shadow kernel reads, so in the
+// drain phase (compact_lists set) the side part waits for shadow(i) instead.
 template <int MODE, bool COUNT>
 static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
-                           const JobParams& job, const LaunchDims& dims, cudaStream_t s, cudaEvent_t* marks,
+                           const JobParams& job, const LaunchDims& dims, const IterStreams& st, cudaEvent_t* marks,
                            int* compact_lists) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
-    auto mark = [&](int i) { if (marks) cudaEventRecord(marks[i], s); };
-    mark(0);
-    k_prepare<<<1, 32, 0, s>>>(ctl, dims.compact_quarters);
+    cudaStream_t s = st.main, side = st.overlap ? st.side : st.main;
+    auto mark = [&](int i, cudaStream_t on) { if (marks) cudaEventRecord(marks[i], on); };
+    if (st.overlap) cudaStreamWaitEvent(side, st.fork, 0);
+    mark(0, side);
+    k_prepare<<<1, 32, 0, side>>>(ctl, dims.compact_quarters);
     if (compact_lists) {  // the host launches these only once the job is close to its drain phase
         int* list_a = compact_lists;
         int* list_b = compact_lists + pool.capacity / 2 + 512;
-        k_compact_scan<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b);
-        k_compact_move<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b);
-        k_compact_commit<<<1, 32, 0, s>>>(ctl);
+        k_compact_scan<<<persistent, kBlock, 0, side>>>(pool, ctl, list_a, list_b);
+        k_compact_move<<<persistent, kBlock, 0, side>>>(pool, ctl, list_a, list_b);
+        k_compact_commit<<<1, 32, 0, side>>>(ctl);
     }
     // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
-    // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up
-    const int regen_blocks = min(full, max(persistent, full / 4));
-    k_regen<<<regen_blocks, kBlock, 0, s>>>(pool, free_list, ctl, job);
-    mark(1);
+    // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up;
+    // small CTAs so that one fits beside the persistent shadow CTA of an SM
+    const int kRegenBlock = dims.regen_block;
+    const int regen_full = (pool.capacity + kRegenBlock - 1) / kRegenBlock;
+    const int regen_blocks = min(regen_full, max(2 * persistent, regen_full / 4));
+    k_regen<<<regen_blocks, kRegenBlock, 0, side>>>(pool, free_list, ctl, job);
+    mark(1, side);
+    if (st.overlap) {
+        cudaEventRecord(st.join, side);
+        cudaStreamWaitEvent(s, st.join, 0);
+    }
+    mark(2, s);
     if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
-    mark(2);
+    mark(3, s);
     k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<full, kBlock, 0, s>>>(pool, free_list, ctl, sc, job);
-    mark(3);
+    mark(4, s);
+    if (st.overlap && !compact_lists) cudaEventRecord(st.fork, s);  // the next side part may start now
     if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
-    mark(4);
+    mark(5, s);
+    if (st.overlap && compact_lists) cudaEventRecord(st.fork, s);
 }
 
 void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
-                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, cudaStream_t s,
+                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, const IterStreams& st,
                   cudaEvent_t* marks, int* compact_lists) {
     if (traversal == TRT_TRAVERSE_REF) {
-        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
-        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
+        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
+        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
     } else {
-        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
-        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, s, marks, compact_lists);
+        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
+        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
     }
 }
 

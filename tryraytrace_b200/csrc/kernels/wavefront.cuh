@@ -78,6 +78,7 @@ struct LaunchDims {
     int fast_threads;   // threads of the persistent traversal CTAs (one CTA per SM): 512, 768 or 1024
     int smem_nodes;     // wide nodes staged into shared memory per CTA (top of the tree)
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
+    int regen_block;    // threads per regenerate CTA (it shares SMs with the persistent shadow CTAs)
     int compact_quarters;  // drain phase: compact when live paths <= this many quarters of the visited slots (1..3)
     Phases closest_phases, shadow_phases;
 };
@@ -93,11 +94,19 @@ void wf_reset_counters(Control* ctl, cudaStream_t s);
 void wf_begin_job(Control* ctl, unsigned long long total_samples, int pool_capacity, cudaStream_t s);
 void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_frame_seed, int frame_stride,
                   int seed_base, int n_frames, XwColVec* out, cudaStream_t s);
-// one wavefront iteration (five kernels) on stream s
-// `marks`, when not null, receives five events recorded at the kernel boundaries of the
-// iteration: [prepare+regenerate] m1 [extend] m2 [shade] m3 [shadow] m4  (m0 first).
+// Streams of an iteration: everything runs on `main`; with `overlap` the prepare/regenerate part of
+// the next iteration runs on `side`, forked from main after the shade kernel (event `fork`) and
+// joined before the next extend kernel (event `join`).  The caller records `fork` on main once
+// before the first iteration of a job.
+struct IterStreams {
+    cudaStream_t main, side;
+    cudaEvent_t fork, join;
+    bool overlap;
+};
+// one wavefront iteration on the streams of `st`
+// `marks`, when not null, receives six events: [0] prepare+regenerate [1]  and  [2] extend [3] shade [4] shadow [5]
 void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
-                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, cudaStream_t s,
+                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, const IterStreams& st,
                   cudaEvent_t* marks = nullptr, int* compact_lists = nullptr);
 // one-time opt-in to large dynamic shared memory for the persistent kernels
 int wf_configure();
