@@ -237,7 +237,7 @@ int alloc_pool(int cap, bool with_free_list, void** mem, PoolView* pool, int** f
 }
 
 int ensure_pool(trt_ctx* c, int cap) {
-    cap = std::max(256, (cap + 255) & ~255);
+    cap = std::max(512, (cap + 511) & ~511);
     if (c->pool_cap == cap) return 0;
     cudaFree(c->pool_mem);
     cudaFree(c->d_compact);
@@ -282,6 +282,8 @@ LaunchDims launch_dims(const trt_ctx* c) {
     if (const char* e = getenv("TRT_SMEM_NODES")) d.smem_nodes = std::max(0, std::min(fit, atoi(e)));
     d.refill_below = 32;
     d.regen_block = 128;
+    d.shade_block = 512;
+    if (const char* e = getenv("TRT_SHADE_BLOCK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512) d.shade_block = v; }
     if (const char* e = getenv("TRT_REGEN_BLOCK")) d.regen_block = std::max(32, std::min(256, atoi(e) / 32 * 32));
     d.compact_quarters = 3;
     if (const char* e = getenv("TRT_COMPACT_QUARTERS")) d.compact_quarters = std::max(1, std::min(3, atoi(e)));

@@ -16,6 +16,7 @@ namespace trt {
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kShadeMaxBlock = 512;
 constexpr int kCompactMinCap = 32 * 1024;  // the pool is not compacted below this many slots
 
 TRT_DEV int pack_flags(int state, int depth, int mode) { return state | (depth << 8) | (mode << 16); }
@@ -64,7 +65,7 @@ __global__ void k_prepare(Control* ctl, int compact_quarters) {
     const bool go = n_regen == 0 && ctl->next_sample == ctl->total_samples && cap > kCompactMinCap && (long long)ctl->alive * 4 <= (long long)cap * compact_quarters;
     ctl->compact_go = go ? 1 : 0;
     if (go) {
-        ctl->compact_new_cap = max(kCompactMinCap, (ctl->alive + kBlock - 1) / kBlock * kBlock);
+        ctl->compact_new_cap = max(kCompactMinCap, (ctl->alive + kShadeMaxBlock - 1) / kShadeMaxBlock * kShadeMaxBlock);
         ctl->compact_a = ctl->compact_b = 0;
     }
 }
@@ -260,10 +261,10 @@ __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev s
 // requested up front, before the state word has come back; in the drain phase of a job, when
 // most slots are dead, the loads wait for the state check instead.
 template <bool COUNT, bool FAST>
-__global__ void __launch_bounds__(kBlock) k_shade(PoolView pool, int* __restrict__ free_list, Control* ctl,
+__global__ void __launch_bounds__(kShadeMaxBlock) k_shade(PoolView pool, int* __restrict__ free_list, Control* ctl,
                                                   SceneDev sc, JobParams job) {
-    __shared__ int scratch[2 + kBlock / 32];
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of kBlock
+    __shared__ int scratch[2 + kShadeMaxBlock / 32];
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of the block size
     const int cap = ctl->active_cap;                         // ... and so is the compacted bound
     if (slot == 0) ctl->cursor_shadow = 0;                   // the shadow kernel of this iteration starts at chunk 0
     if (blockIdx.x * blockDim.x >= cap) return;              // whole block beyond the visited prefix
@@ -988,7 +989,7 @@ static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, c
     if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(3, s);
-    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<full, kBlock, 0, s>>>(pool, free_list, ctl, sc, job);
+    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<pool.capacity / dims.shade_block, dims.shade_block, 0, s>>>(pool, free_list, ctl, sc, job);
     mark(4, s);
     if (st.overlap && !compact_lists) cudaEventRecord(st.fork, s);  // the next side part may start now
     if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);

@@ -78,6 +78,8 @@ struct LaunchDims {
     int fast_threads;   // threads of the persistent traversal CTAs (one CTA per SM): 512, 768 or 1024
     int smem_nodes;     // wide nodes staged into shared memory per CTA (top of the tree)
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
+    int shade_block;    // threads per shade CTA (64 .. 512; the pool capacity is a multiple of 512): larger CTAs, fewer
+                        // free-list atomics and barriers waiting on them
     int regen_block;    // threads per regenerate CTA (it shares SMs with the persistent shadow CTAs)
     int compact_quarters;  // drain phase: compact when live paths <= this many quarters of the visited slots (1..3)
     Phases closest_phases, shadow_phases;
