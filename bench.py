@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP)
-    ap.add_argument("--pool", type=int, default=4 << 20, help="wavefront pool size (paths in flight)")
+    ap.add_argument("--pool", type=int, default=8 << 20, help="wavefront pool size (paths in flight)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -188,7 +188,7 @@ def main():
     config = {"workload": workload, "spp_per_step": args.spp, "width": w, "height": h,
               "sharding": f"sample index, stride {world}, one all-reduce of the accumulation buffer per step" if world > 1
               else "single GPU", "l2": "no explicit L2 flush: each step streams the wavefront pool "
-              "(>600 MB of path state) and the 33 MB accumulation buffer, both larger than or comparable to the 126 MB L2"}
+              "(1.1 GB of path state) and the 33 MB accumulation buffer, both larger than or comparable to the 126 MB L2"}
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":

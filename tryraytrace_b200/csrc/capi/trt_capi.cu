@@ -363,13 +363,17 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if ((long long)o.seed_base + first < 0) return fail(TRT_ERR_ARG, "negative RNG seed");
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_rng_tables(c, w, h)) return rc;
-    // pool_paths = 0: size the pool to the job -- about a sixth of its samples in flight, between
-    // 256 Ki and 4 Mi slots (B200 sweeps: 1 Mi is best for the 4.9 M samples of C1, 4 Mi from C2 up)
+    // pool_paths = 0: size the pool to the job -- a sixteenth of the samples of one job (at most
+    // kFrameChunk frames) in flight, between 256 Ki and 16 Mi slots (B200 sweeps with drain compaction and
+    // overlapped regeneration: 512 Ki..1 Mi for the 4.9 M samples of C1, 8 Mi for C2 at 64 spp, 16 Mi at 4K)
     int pool_paths = o.pool_paths;
     if (pool_paths == 0) {
-        const unsigned long long want = (unsigned long long)w * h * (unsigned long long)n_frames / 6;
+        const unsigned long long want =
+            (unsigned long long)w * h * (unsigned long long)std::min(n_frames, kFrameChunk) / 16;
         pool_paths = 256 << 10;
-        while (pool_paths < (4 << 20) && (unsigned long long)pool_paths < want) pool_paths <<= 1;
+        while (pool_paths < (16 << 20) && (unsigned long long)pool_paths < want) pool_paths <<= 1;
+        // ... but at least 1 Mi when the job has that many samples (C1: 1 Mi beats 512 Ki by 7 %)
+        while (pool_paths < (1 << 20) && (unsigned long long)pool_paths < want * 16) pool_paths <<= 1;
     }
     if (int rc = ensure_pool(c, pool_paths)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
