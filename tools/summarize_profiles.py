@@ -28,7 +28,7 @@ rep = ROOT / "gpurun_out" / f"prof_{tag}.ncu-rep"
 if rep.exists():
     txt = subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), str(rep)], capture_output=True, text=True).stdout
     (out / f"{tag}_ncu_full_summary.txt").write_text(
-        "# ncu --set full --clock-control none --import-source on, kernels of one bench step (C2, 1080p, pool 4 Mi)\n" + txt)
+        "# ncu --set full --clock-control none --import-source on, kernels of one bench step (C2, 1080p, bench.py default pool)\n" + txt)
     print(txt)
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
