@@ -109,3 +109,11 @@ def test_open_scene_with_short_paths_drains_correctly(trt, ref, ctx, assets):
     for pool in (1 << 16, 1 << 18):
         a = radiance_gate(trt, ref, ctx, sc, cam, w, h, 6, f"C5 2x2 pool {pool}", pool_paths=pool)
         assert float(a.sum()) > 0
+
+
+def test_render_longer_than_one_job(trt, ref, ctx, assets):
+    """130 frames = three wavefront jobs (64 + 64 + 2 frames) on one stream pair: every job drains,
+    compacts and hands the side stream back before the next one starts."""
+    sc = trt.HostScene.from_config(1, assets)
+    cam, w, h = trt.config_camera(1, 96, 64)
+    radiance_gate(trt, ref, ctx, sc, cam, w, h, 130, "C1 96x64, 130 frames")

@@ -29,19 +29,17 @@ TRT_DEV int block_append(bool want, int* counter, int* smem_scratch /* >= 2 + wa
     const int rank = __popc(m & ((1u << lane) - 1u));
     if (lane == 0) smem_scratch[2 + warp] = __popc(m);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int total = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
-            const int c = smem_scratch[2 + w];
-            smem_scratch[2 + w] = total;
-            total += c;
-        }
-        smem_scratch[0] = total ? atomicAdd(counter, total) : 0;
+    // every warp sums the counts of the warps before it (lane w reads warp w's count); warp 0 also
+    // has the block total and claims the range with the one atomic
+    const int n_warps = (int)(blockDim.x >> 5);
+    const int c = (int)lane < n_warps ? smem_scratch[2 + lane] : 0;
+    const int before = __reduce_add_sync(0xffffffffu, lane < warp ? c : 0);
+    if (warp == 0) {
+        const int total = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0) smem_scratch[0] = total ? atomicAdd(counter, total) : 0;
     }
     __syncthreads();
-    const int idx = smem_scratch[0] + smem_scratch[2 + warp] + rank;
-    __syncthreads();  // scratch is reused by the next append
-    return idx;
+    return smem_scratch[0] + before + rank;  // called once per kernel: the scratch is not reused
 }
 
 // ---- prepare: single thread, advances the queue bookkeeping between iterations --------
