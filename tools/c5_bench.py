@@ -31,7 +31,7 @@ ctx.init_scene_data(objs, [], None, lights, builder=trt.BUILD_DEVICE_LBVH)  # se
 out["device_build_ms_warm"] = round(ctx.scene_info()["build_ms"], 2)
 out["wide_nodes"], out["wide_depth"] = info["n_wide_nodes"], info["wide_depth"]
 acc = torch.zeros(w * h * 4, device="cuda")
-o = trt.default_opts(pool_paths=4 << 20)
+o = trt.default_opts()  # pool sized to the job by the library
 ctx.render(acc, w, h, 1, 1, cam, o); ctx.synchronize()
 ctx.reset_counters()
 ctx.render(acc, w, h, 2, spp, cam, o); ctx.synchronize()

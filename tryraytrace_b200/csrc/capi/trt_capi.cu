@@ -70,6 +70,7 @@ struct trt_ctx {
     int* d_lights = nullptr;
     float4* d_wide_nodes = nullptr;
     float4* d_tris = nullptr;
+    bool wide_from_pool = false;  // d_wide_nodes / d_tris came from the stream-ordered pool (device builder)
     std::vector<cudaArray_t> tex_arrays;
     std::vector<cudaTextureObject_t> tex_objs;
     SceneDev sc{};
@@ -129,8 +130,14 @@ void free_scene(trt_ctx* c) {
     cudaFree(c->d_objects);
     cudaFree(c->d_ref_nodes);
     cudaFree(c->d_lights);
-    cudaFree(c->d_wide_nodes);
-    cudaFree(c->d_tris);
+    if (c->wide_from_pool) {
+        cudaFreeAsync(c->d_wide_nodes, c->stream);
+        cudaFreeAsync(c->d_tris, c->stream);
+    } else {
+        cudaFree(c->d_wide_nodes);
+        cudaFree(c->d_tris);
+    }
+    c->wide_from_pool = false;
     c->d_objects = c->d_ref_nodes = c->d_wide_nodes = c->d_tris = nullptr;
     c->d_lights = nullptr;
     c->have_scene = false;
@@ -596,13 +603,14 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
         if (const char* e = getenv("TRT_TOP_SAH")) top_sah = atoi(e) != 0;
         if (build_wide_bvh_device(c->d_objects, n_objects, c->d_ref_nodes, have_ref ? n_nodes : 0, max_leaf, top_sah, &dw,
                                   c->stream, &err) != 0) {
-            cudaFree(dw.d_nodes);
-            cudaFree(dw.d_tris);
+            cudaFreeAsync(dw.d_nodes, c->stream);
+            cudaFreeAsync(dw.d_tris, c->stream);
             cudaGetLastError();
             return fail(TRT_ERR_CUDA, "device BVH build: %s", err.c_str());
         }
         c->d_wide_nodes = dw.d_nodes;
         c->d_tris = dw.d_tris;
+        c->wide_from_pool = true;
         tp = dw.top;
         n_wide = dw.n_nodes; n_tris = dw.n_tris; n_top = dw.n_top; depth = dw.depth; n_underivable = dw.n_underivable;
         build_ms = dw.build_ms;

@@ -552,15 +552,28 @@ struct TopSah {
     }
 };
 
-struct Scratch {  // frees everything it allocated when it goes out of scope
+// Scratch buffers come from the device's stream-ordered memory pool: the build needs ~300 bytes per
+// primitive for a few milliseconds, and cudaMalloc / cudaFree of gigabytes (with their device-wide
+// synchronisation and page mapping) used to cost more than the kernels; the pool keeps the memory
+// for the next build of the process.  Everything is released when the object goes out of scope.
+struct Scratch {
+    cudaStream_t stream;
     std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s) : stream(s) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;  // do not hand the memory back to the driver between builds
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     ~Scratch() {
-        for (void* p : ptrs) cudaFree(p);
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
     }
     template <class T>
     cudaError_t get(T** p, size_t count) {
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), stream);
         if (e == cudaSuccess) ptrs.push_back(q);
         *p = (T*)q;
         return e;
@@ -582,7 +595,7 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
                           bool top_sah, DeviceWideBvh* out, cudaStream_t s, std::string* err) {
     max_leaf = std::max(1, std::min(4, max_leaf));
     *out = DeviceWideBvh();
-    Scratch tmp;
+    Scratch tmp(s);
     cudaEvent_t ev0, ev1;
     BCU(cudaEventCreate(&ev0));
     BCU(cudaEventCreate(&ev1));
@@ -614,8 +627,8 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
     out->top.root_lo = make_float4(inf, inf, inf, 0.f);
     out->top.root_hi = make_float4(-inf, -inf, -inf, 0.f);
     if (n_live == 0) {  // nothing can be hit: one empty node
-        BCU(cudaMalloc(&out->d_nodes, 128));
-        BCU(cudaMalloc(&out->d_tris, 48));
+        BCU(cudaMallocAsync(&out->d_nodes, 128, s));
+        BCU(cudaMallocAsync(&out->d_tris, 48, s));
         const float4 empty[8] = {make_float4(inf, inf, inf, inf), make_float4(-inf, -inf, -inf, -inf),
                                  make_float4(inf, inf, inf, inf), make_float4(-inf, -inf, -inf, -inf),
                                  make_float4(inf, inf, inf, inf), make_float4(-inf, -inf, -inf, -inf),
@@ -706,7 +719,7 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
     const int* sorted = idx_b;  // the first n_rest entries are the tree's objects in Morton order
 
     // 4. triangle records in leaf order
-    BCU(cudaMalloc(&out->d_tris, (size_t)std::max(n_rest, 1) * 48));
+    BCU(cudaMallocAsync(&out->d_tris, (size_t)std::max(n_rest, 1) * 48, s));
     out->n_tris = n_rest;
     k_tri_records<<<grid(n_rest), kB, 0, s>>>(d_objects, sorted, flags, n_rest, out->d_tris);
 
@@ -720,7 +733,7 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
     float4* d_root;  // root_lo, root_hi
     BCU(tmp.get(&d_root, 2));
     if (n_rest <= max_leaf) {
-        BCU(cudaMalloc(&out->d_nodes, 128));
+        BCU(cudaMallocAsync(&out->d_nodes, 128, s));
         k_single_leaf<<<1, 32, 0, s>>>(tv, n_rest, out->d_nodes, d_root, d_root + 1);
         out->n_nodes = 1;
         out->depth = 1;
@@ -828,7 +841,7 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
         }
         out->n_nodes = h_cnt[1];
         out->depth = h_cnt[2];
-        BCU(cudaMalloc(&out->d_nodes, (size_t)out->n_nodes * 128));
+        BCU(cudaMallocAsync(&out->d_nodes, (size_t)out->n_nodes * 128, s));
         BCU(cudaMemcpyAsync(out->d_nodes, wide_tmp, (size_t)out->n_nodes * 128, cudaMemcpyDeviceToDevice, s));
         BCU(cudaMemcpyAsync(d_root, ilo + root_ref, 16, cudaMemcpyDeviceToDevice, s));
         BCU(cudaMemcpyAsync(d_root + 1, ihi + root_ref, 16, cudaMemcpyDeviceToDevice, s));

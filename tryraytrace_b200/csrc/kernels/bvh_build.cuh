@@ -17,7 +17,7 @@
 namespace trt {
 
 struct DeviceWideBvh {
-    float4* d_nodes = nullptr;  // n_nodes x 128 B (cudaMalloc, owned by the caller after return)
+    float4* d_nodes = nullptr;  // n_nodes x 128 B (cudaMallocAsync on `s`: free with cudaFreeAsync; owned by the caller)
     float4* d_tris = nullptr;   // n_tris x 48 B
     int n_nodes = 0, n_tris = 0;
     TopPrims top{};             // root-level list + tree bounds, ready to hand to the kernels
