@@ -4,7 +4,11 @@ import torch
 
 
 def dev_zeros(n, dtype):
-    return torch.zeros(n, dtype=dtype, device="cuda")
+    """Device buffer handed to the library, which works on its OWN (non-blocking) stream: the fill
+    that torch enqueues on its stream has to be complete before the library may touch the buffer."""
+    t = torch.zeros(n, dtype=dtype, device="cuda")
+    torch.cuda.synchronize()
+    return t
 
 
 def psnr_8bit(a_argb, b_argb):

@@ -38,6 +38,7 @@ def random_rays(n, seed, lo=(0, 0, 0), hi=(100, 100, 300)):
     rays[:, 3:6] = d / d.norm(dim=1, keepdim=True)
     rays[:, 6] = torch.rand(n, generator=g, device="cuda") * 150 + 1
     rays[: n // 50, 3] = 0.0
+    torch.cuda.synchronize()  # the library reads the rays on its own stream
     return rays
 
 

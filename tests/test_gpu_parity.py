@@ -122,6 +122,7 @@ def test_secondary_rays_fast_equals_reference_order(trt, ref, ctx, scenes, confi
     rays[:, 3:6] = d / d.norm(dim=1, keepdim=True)
     rays[:, 6] = torch.rand(n, generator=g, device="cuda") * 150 + 1
     rays[: n // 50, 3] = 0.0  # axis-parallel directions exercise the safe_inv / infinite-reciprocal paths
+    torch.cuda.synchronize()  # the library reads the rays on its own stream
     out = {}
     for mode in (trt.TRAVERSE_REF, trt.TRAVERSE_FAST):
         i, t, o = dev_zeros(n, torch.int32), dev_zeros(n, torch.float32), dev_zeros(n, torch.int32)

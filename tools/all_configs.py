@@ -19,6 +19,7 @@ for config in (1, 2, 3, 4):
     spp = min(trt.CONFIGS[config]["spp"], cap)
     ctx.upload(sc)
     acc = torch.zeros(w * h * 4, device="cuda")
+    torch.cuda.synchronize()  # the library works on its own stream
     o = trt.default_opts()  # pool sized to the job by the library
     ctx.render(acc, w, h, 1, 4, cam, o); ctx.synchronize()
     ctx.reset_counters()
@@ -32,6 +33,7 @@ for config in (1, 2, 3, 4):
     if reflib.available():
         reflib.init_scene(sc)
         a2, st = torch.zeros_like(acc), torch.zeros_like(acc)
+        torch.cuda.synchronize()
         rspp = min(spp, 16)
         reflib.render_frames(a2, st, w, h, 1, 2, cam, 1)
         torch.cuda.synchronize()

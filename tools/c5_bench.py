@@ -31,6 +31,7 @@ ctx.init_scene_data(objs, [], None, lights, builder=trt.BUILD_DEVICE_LBVH)  # se
 out["device_build_ms_warm"] = round(ctx.scene_info()["build_ms"], 2)
 out["wide_nodes"], out["wide_depth"] = info["n_wide_nodes"], info["wide_depth"]
 acc = torch.zeros(w * h * 4, device="cuda")
+torch.cuda.synchronize()  # the library works on its own stream
 o = trt.default_opts()  # pool sized to the job by the library
 ctx.render(acc, w, h, 1, 1, cam, o); ctx.synchronize()
 ctx.reset_counters()
@@ -52,6 +53,7 @@ if ref_build:
         ctx.close()
         reflib.init_scene(sc)
         stage = torch.zeros_like(acc)
+        torch.cuda.synchronize()
         reflib.render_frames(acc, stage, w, h, 1, 1, cam, 1)
         torch.cuda.synchronize()
         t0 = time.time()

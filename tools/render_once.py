@@ -18,6 +18,7 @@ cam, w, h = trt.config_camera(config)
 ctx = trt.Context(0)
 ctx.upload(sc)
 acc = torch.zeros(w * h * 4, device="cuda")
+torch.cuda.synchronize()  # the library works on its own stream
 trav = trt.TRAVERSE_REF if mode == "ref" else trt.TRAVERSE_FAST
 o = trt.default_opts(traversal=trav, pool_paths=pool)
 if warm:
