@@ -183,8 +183,11 @@ int trt_reset_counters(trt_ctx* ctx);
 int trt_last_render_ms(trt_ctx* ctx, float* ms);
 int trt_kernel_times_get(trt_ctx* ctx, trt_kernel_times* out);
 /* The CUDA stream (cudaStream_t) the context launches on, and a way to make it launch on a
- * caller-owned stream instead (NULL restores the context's own stream).  The reference
- * launches on the legacy default stream (src/renderer.cu:769). */
+ * caller-owned stream instead (NULL restores the context's own stream).  The context's own stream
+ * is non-blocking: buffers the caller fills on another stream must be complete (or ordered by
+ * the caller) before a call that reads them.  The reference launches on the legacy default
+ * stream (src/renderer.cu:769); the C++ drop-in entry points of include/renderer.h do the same
+ * (trt_set_stream(ctx, cudaStreamLegacy)). */
 void* trt_stream(trt_ctx* ctx);
 int trt_set_stream(trt_ctx* ctx, void* cuda_stream);
 

@@ -4,6 +4,7 @@
 #include "renderer.h"
 #include "image_io.h"
 #include "trt_capi.h"
+#include <cuda_runtime_api.h>
 #include <cstdio>
 #include <cstdlib>
 
@@ -17,6 +18,11 @@ trt_ctx* global_ctx() {
         if (trt_create(dev, &g_ctx) != 0) {
             std::fprintf(stderr, "[Renderer Error] %s\n", trt_last_error());
             g_ctx = nullptr;
+        } else {
+            // The reference launches on the legacy default stream (src/renderer.cu:769) and its caller relies
+            // on that: cudaMemset of the accumulation buffer before, a device-to-device snapshot right after
+            // (src/main.cpp:172, :188), both on the legacy stream.  The drop-in entry points keep that order.
+            trt_set_stream(g_ctx, (void*)cudaStreamLegacy);
         }
     }
     return g_ctx;
