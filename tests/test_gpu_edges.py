@@ -112,8 +112,8 @@ def test_open_scene_with_short_paths_drains_correctly(trt, ref, ctx, assets):
 
 
 def test_render_longer_than_one_job(trt, ref, ctx, assets):
-    """130 frames = three wavefront jobs (64 + 64 + 2 frames) on one stream pair: every job drains,
+    """600 frames = three wavefront jobs (256 + 256 + 88 frames) on one stream pair: every job drains,
     compacts and hands the side stream back before the next one starts."""
     sc = trt.HostScene.from_config(1, assets)
     cam, w, h = trt.config_camera(1, 96, 64)
-    radiance_gate(trt, ref, ctx, sc, cam, w, h, 130, "C1 96x64, 130 frames")
+    radiance_gate(trt, ref, ctx, sc, cam, w, h, 600, "C1 96x64, 600 frames")

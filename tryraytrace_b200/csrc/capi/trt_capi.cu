@@ -45,7 +45,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(TRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-int kFrameChunk = 64;                 // frames per wavefront job (bounds the column-vector table); TRT_FRAME_CHUNK overrides
+int kFrameChunk = 256;                // frames per wavefront job (bounds the column-vector table); TRT_FRAME_CHUNK overrides
 constexpr int kBatchIterations = 16;  // iterations issued between completion polls
 constexpr int kWideStackEntries = 128;  // kernels/traverse_fast.cuh kSpillEntries
 constexpr int kAutoDeviceBuildAbove = 1 << 18;  // TRT_BUILD_AUTO: objects above which the device builder is used
