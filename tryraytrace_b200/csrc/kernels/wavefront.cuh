@@ -2,10 +2,12 @@
 // launch interface implemented in wavefront.cu.
 //
 // A fixed pool of P path slots lives in HBM.  Every iteration runs
-//     prepare -> regenerate -> extend (closest hit) -> shade -> shadow (any hit)
-// over the pool.  Paths that end are accumulated into the caller's buffer and their slots
+//     prepare -> [compact] -> regenerate -> extend (closest hit) -> shade -> shadow (any hit)
+// over the pool (prepare/regenerate of the next iteration on a side stream, behind the shadow
+// kernel).  Paths that end are accumulated into the caller's buffer and their slots
 // go to a free list; `regenerate` refills those slots with the next camera samples of the
-// job, so the extend kernel always sees a full pool until the job drains.  Shadow rays are
+// job, so the extend kernel always sees a full pool until the job drains; in the drain phase the
+// live slots are compacted into a prefix of the pool (active_cap).  Shadow rays are
 // written IN PLACE (one per slot, a valid flag in sh_d.w): almost every diffuse vertex
 // spawns one, so compaction would buy nothing, and the persistent traversal kernels pull
 // 32-slot chunks of either ray array with TMA bulk copies.  The next-event contribution
@@ -21,16 +23,17 @@ enum { SLOT_DEAD = 0, SLOT_ACTIVE = 1, SLOT_FINISH = 2 };
 
 // Path slot, SoA: 128 bytes per slot over all arrays.
 struct PoolView {
-    float4* ray_o;   // origin.xyz, length of the slot's shadow ray (it starts at the same point)
+    float4* ray_o;   // origin.xyz, length of the slot's shadow ray (it starts at the same point); for a fresh
+                     // camera ray (depth 0) .w carries the pixel index instead (thr / rad are not written yet)
     float4* ray_d;   // direction.xyz, flags (int bits): state | depth << 8 | prev_mode << 16
-    float2* hit;     // written by extend: t, hit object id (int bits, -1 = miss)
+    float2* hit;     // written by extend: t, hit object id | kTriNoDerive (int bits, -1 = miss); verified by shade
     float4* thr;     // throughput.xyz, pixel index (int bits)
     float4* rad;     // radiance.xyz, unused
     float4* pend;    // next-event contribution of the previous vertex (throughput applied), unused
     float4* sh_d;    // shadow ray of this slot: direction.xyz, valid flag (int bits, 1 = trace it)
     uint4* rng_a;    // XORWOW v0..v3
     uint2* rng_b;    // XORWOW v4, d
-    int capacity;    // multiple of 256
+    int capacity;    // multiple of 256 (512 for the render pool: the shade CTA size)
 };
 
 // Device-resident control block (one per context).
