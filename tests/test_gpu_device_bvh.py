@@ -137,3 +137,27 @@ def test_c5_small_field_device_vs_host_builder(trt, ref, scenes):
         assert bad == 0
     finally:
         c.close()
+
+
+def test_c5_field_incoherent_rays_device_tree_equals_reference_order(trt, scenes):
+    """C5 at a 6 x 6 grid (228 k triangles), rays scattered through the field: closest hits and shadow
+    bits over the device-built tree (hybrid LBVH / SAH top levels) equal the reference-order traversal."""
+    sc = scenes.get(5, grid=6)
+    c = trt.Context(0)
+    try:
+        c.upload(sc, builder=trt.BUILD_DEVICE_LBVH)
+        n = 500_000
+        rays = random_rays(n, 77, lo=(-200, 0.05, -20), hi=(-100, 12, 80))
+        out = {}
+        for mode in (trt.TRAVERSE_REF, trt.TRAVERSE_FAST):
+            i, t, o = dev_zeros(n, torch.int32), dev_zeros(n, torch.float32), dev_zeros(n, torch.int32)
+            c.trace_closest(rays, n, mode, i, t)
+            c.trace_shadow(rays, n, mode, o)
+            out[mode] = (i, t, o)
+        a, b = out[trt.TRAVERSE_REF], out[trt.TRAVERSE_FAST]
+        hit_mesh = float((a[0] >= 2).float().mean())  # ids 0/1 are the floor and the light in the sorted array or not; any id counts
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1].view(torch.int32), b[1].view(torch.int32))
+        assert torch.equal(a[2], b[2])
+        assert float((a[0] >= 0).float().mean()) > 0.3 and hit_mesh > 0.05
+    finally:
+        c.close()
