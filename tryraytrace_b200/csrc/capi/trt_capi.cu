@@ -45,7 +45,7 @@ int fail(int code, const char* fmt, ...) {
             return fail(TRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-int kFrameChunk = 256;                // frames per wavefront job (bounds the column-vector table); TRT_FRAME_CHUNK overrides
+constexpr int kFrameChunkDefault = 256;  // frames per wavefront job (bounds the column-vector table); TRT_FRAME_CHUNK overrides
 constexpr int kBatchIterations = 16;  // iterations issued between completion polls
 constexpr int kWideStackEntries = 128;  // kernels/traverse_fast.cuh kSpillEntries
 constexpr int kAutoDeviceBuildAbove = 1 << 18;  // TRT_BUILD_AUTO: objects above which the device builder is used
@@ -370,6 +370,8 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if ((long long)o.seed_base + first < 0) return fail(TRT_ERR_ARG, "negative RNG seed");
     if (int rc = use_device(c)) return rc;
     if (int rc = ensure_rng_tables(c, w, h)) return rc;
+    int kFrameChunk = kFrameChunkDefault;
+    if (const char* e = getenv("TRT_FRAME_CHUNK")) kFrameChunk = std::max(1, std::min(1024, atoi(e)));
     // pool_paths = 0: size the pool to the job -- a sixteenth of the samples of one job (at most
     // kFrameChunk frames) in flight, between 256 Ki and 16 Mi slots (B200 sweeps with drain compaction and
     // overlapped regeneration: 512 Ki..1 Mi for the 4.9 M samples of C1, 8 Mi for C2 at 64 spp, 16 Mi at 4K)
@@ -385,7 +387,6 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_pool(c, pool_paths)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
-    if (const char* e = getenv("TRT_FRAME_CHUNK")) kFrameChunk = std::max(1, std::min(1024, atoi(e)));
     c->marks_used = 0;
     IterStreams st{c->stream, c->side_stream, c->ev_fork, c->ev_join, true};
     if (const char* e = getenv("TRT_OVERLAP")) st.overlap = atoi(e) != 0;
