@@ -49,7 +49,8 @@ typedef struct {
     int pool_paths;     /* wavefront pool size (paths in flight); 0 = sized to the job (256 Ki .. 16 Mi) */
     int count_rays;     /* 1 = also count node fetches / triangle tests (small cost); ray
                            and sample counts are always maintained */
-    int time_kernels;   /* 1 = record CUDA events at every kernel boundary (see trt_kernel_times) */
+    int time_kernels;   /* 1 = record CUDA events at every kernel boundary (see trt_kernel_times);
+                         * 2 = only around the closest-hit traversal kernel (the other fields stay 0) */
     int reserved[1];
 } trt_opts;
 

@@ -102,6 +102,7 @@ struct trt_ctx {
     // per-kernel timing (trt_opts.time_kernels)
     std::vector<cudaEvent_t> marks;  // 6 per timed iteration
     size_t marks_used = 0;
+    int marks_mask = 0x3f;
     trt_kernel_times ktimes{};
 
     // scratch accumulation buffer for trt_render_to_host
@@ -389,6 +390,8 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
 
     c->marks_used = 0;
     IterStreams st{c->stream, c->side_stream, c->ev_fork, c->ev_join, true};
+    st.mark_mask = o.time_kernels == 2 ? 0x0c : 0x3f;  // 2: only the marks around the extend kernel
+    c->marks_mask = st.mark_mask;
     if (const char* e = getenv("TRT_OVERLAP")) st.overlap = atoi(e) != 0;
     bool compact = true;
     if (const char* e = getenv("TRT_COMPACT")) compact = atoi(e) != 0;
@@ -858,9 +861,13 @@ int trt_kernel_times_get(trt_ctx* c, trt_kernel_times* out) {
     trt_kernel_times t;
     memset(&t, 0, sizeof(t));
     for (size_t i = 0; i + 6 <= c->marks_used; i += 6) {  // marks: [0] prepare+regenerate [1], [2] extend [3] shade [4] shadow [5]
-        float ms[4];
-        CU(cudaEventElapsedTime(&ms[0], c->marks[i], c->marks[i + 1]));
-        for (int k = 1; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], c->marks[i + k + 1], c->marks[i + k + 2]));
+        float ms[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c->marks_mask == 0x3f) {
+            CU(cudaEventElapsedTime(&ms[0], c->marks[i], c->marks[i + 1]));
+            for (int k = 1; k < 4; k++) CU(cudaEventElapsedTime(&ms[k], c->marks[i + k + 1], c->marks[i + k + 2]));
+        } else {
+            CU(cudaEventElapsedTime(&ms[1], c->marks[i + 2], c->marks[i + 3]));
+        }
         t.regen_ms += ms[0];  // overlaps the previous iteration's shadow kernel unless TRT_OVERLAP=0
         t.extend_ms += ms[1];
         t.shade_ms += ms[2];

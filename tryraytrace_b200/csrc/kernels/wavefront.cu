@@ -960,7 +960,8 @@ static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, c
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
     cudaStream_t s = st.main, side = st.overlap ? st.side : st.main;
-    auto mark = [&](int i, cudaStream_t on) { if (marks) cudaEventRecord(marks[i], on); };
+    // marks[0..5]; st.mark_mask selects which of them are recorded
+    auto mark = [&](int i, cudaStream_t on) { if (marks && ((st.mark_mask >> i) & 1)) cudaEventRecord(marks[i], on); };
     if (st.overlap) cudaStreamWaitEvent(side, st.fork, 0);
     mark(0, side);
     k_prepare<<<1, 32, 0, side>>>(ctl, dims.compact_quarters);

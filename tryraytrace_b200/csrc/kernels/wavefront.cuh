@@ -107,6 +107,7 @@ struct IterStreams {
     cudaStream_t main, side;
     cudaEvent_t fork, join;
     bool overlap;
+    int mark_mask = 0x3f;  // which of the six timing marks of an iteration are recorded
 };
 // one wavefront iteration on the streams of `st`
 // `marks`, when not null, receives six events: [0] prepare+regenerate [1]  and  [2] extend [3] shade [4] shadow [5]
