@@ -1,12 +1,10 @@
 // bvh_build.cu -- see bvh_build.cuh.  LBVH over 63-bit Morton codes of the reference leaf-box
-// centroids (Karras 2012: one thread per internal node finds its key range and split with
+// centroids, sorted by a hand-written stable LSD radix sort (Karras 2012: one thread per internal node finds its key range and split with
 // count-leading-zeros searches; boxes are fitted bottom-up with one atomic counter per node),
 // then a breadth-first collapse into 4-wide nodes (open the inner child with the largest box,
 // like the host builder) with device-side allocation of the output nodes.
 #include "bvh_build.cuh"
 #include "traverse_fast.cuh"
-
-#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -216,6 +214,95 @@ __global__ void k_morton(const float4* __restrict__ lo, const float4* __restrict
         k |= spread21((unsigned long long)v) << (2 - a);
     }
     keys[i] = k;  // 63 bits: strictly below ~0ull
+}
+
+// ---- stable LSD radix sort of (64-bit key, 32-bit value) pairs, 8 bits per pass ---------------------
+// Three kernels per pass.  k_radix_hist: every block counts the digits of its contiguous tile.
+// k_radix_scan: one block turns the (digit-major, block-minor) count table into global offsets.
+// k_radix_scatter: every block walks its tile again in order, 256 keys at a time; a key's rank
+// among the equal digits of its chunk comes from __match_any_sync inside the warp plus per-warp
+// digit counts combined across the eight warps in warp order, which keeps the pass stable.
+constexpr int kRadixBits = 8, kRadixBins = 1 << kRadixBits, kRadixBlock = 256;
+
+__global__ void __launch_bounds__(kRadixBlock) k_radix_hist(const unsigned long long* __restrict__ keys, int n, int tile,
+                                                            int shift, int* __restrict__ table, int n_blocks) {
+    __shared__ int hist[kRadixBins];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int begin = blockIdx.x * tile, end = min(n, begin + tile);
+    for (int i = begin + threadIdx.x; i < end; i += kRadixBlock) atomicAdd(&hist[(int)((keys[i] >> shift) & (kRadixBins - 1))], 1);
+    __syncthreads();
+    table[threadIdx.x * n_blocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+// exclusive scan of `count` ints in place, one block of 1024 threads
+__global__ void __launch_bounds__(1024) k_radix_scan(int* table, int count) {
+    __shared__ int part[1024];
+    const int per = (count + 1023) / 1024;
+    const int begin = threadIdx.x * per, end = min(count, begin + per);
+    int sum = 0;
+    for (int i = begin; i < end; i++) sum += table[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the partial sums
+        const int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (int i = begin; i < end; i++) {
+        const int c = table[i];
+        table[i] = run;
+        run += c;
+    }
+}
+
+__global__ void __launch_bounds__(kRadixBlock) k_radix_scatter(const unsigned long long* __restrict__ keys_in,
+                                                               const int* __restrict__ vals_in, unsigned long long* keys_out,
+                                                               int* vals_out, int n, int tile, int shift,
+                                                               const int* __restrict__ table, int n_blocks) {
+    __shared__ int base[kRadixBins];                    // next output slot of each digit for this block
+    __shared__ int wcount[kRadixBlock / 32][kRadixBins];  // per-warp digit counts of the current chunk
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    base[threadIdx.x] = table[threadIdx.x * n_blocks + blockIdx.x];
+    const int begin = blockIdx.x * tile, end = min(n, begin + tile);
+    for (int chunk = begin; chunk < end; chunk += kRadixBlock) {
+        for (int w = 0; w < kRadixBlock / 32; w++) wcount[w][threadIdx.x] = 0;
+        __syncthreads();
+        const int i = chunk + threadIdx.x;
+        const bool on = i < end;
+        unsigned long long key = 0;
+        int val = 0, digit = 0, rank = 0;
+        if (on) {
+            key = keys_in[i];
+            val = vals_in[i];
+            digit = (int)((key >> shift) & (kRadixBins - 1));
+        }
+        // lanes past the end get a digit of their own class so that they never join a real group
+        const unsigned peers = __match_any_sync(0xffffffffu, on ? digit : kRadixBins + (int)lane);
+        if (on) {
+            rank = __popc(peers & ((1u << lane) - 1u));
+            if (rank == 0) wcount[warp][digit] = __popc(peers);
+        }
+        __syncthreads();
+        {   // thread d: offsets of digit d for the eight warps, in warp order
+            int run = base[threadIdx.x];
+            for (int w = 0; w < kRadixBlock / 32; w++) {
+                const int c = wcount[w][threadIdx.x];
+                wcount[w][threadIdx.x] = run;
+                run += c;
+            }
+            base[threadIdx.x] = run;
+        }
+        __syncthreads();
+        if (on) {
+            const int dst = wcount[warp][digit] + rank;
+            keys_out[dst] = key;
+            vals_out[dst] = val;
+        }
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
@@ -708,12 +795,24 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
     BCU(tmp.get(&idx_a, n));
     BCU(tmp.get(&idx_b, n));
     k_morton<<<grid(n), kB, 0, s>>>(olo, ohi, flags, n, cmin, scale, keys_a, idx_a);
-    {
-        size_t bytes = 0;
-        BCU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 64, s));
-        char* d_tmp;
-        BCU(tmp.get(&d_tmp, bytes));
-        BCU(cub::DeviceRadixSort::SortPairs(d_tmp, bytes, keys_a, keys_b, idx_a, idx_b, n, 0, 64, s));
+    {   // 63-bit keys (and the all-ones key of excluded objects): eight 8-bit passes, ping-pong a <-> b
+        const int n_blocks = std::max(1, std::min(1024, (n + 4095) / 4096));
+        const int tile = ((n + n_blocks - 1) / n_blocks + kRadixBlock - 1) / kRadixBlock * kRadixBlock;
+        int* table;
+        BCU(tmp.get(&table, (size_t)kRadixBins * n_blocks));
+        unsigned long long *kin = keys_a, *kout = keys_b;
+        int *vin = idx_a, *vout = idx_b;
+        for (int pass = 0; pass < 8; pass++) {
+            const int shift = pass * kRadixBits;
+            k_radix_hist<<<n_blocks, kRadixBlock, 0, s>>>(kin, n, tile, shift, table, n_blocks);
+            k_radix_scan<<<1, 1024, 0, s>>>(table, kRadixBins * n_blocks);
+            k_radix_scatter<<<n_blocks, kRadixBlock, 0, s>>>(kin, vin, kout, vout, n, tile, shift, table, n_blocks);
+            std::swap(kin, kout);
+            std::swap(vin, vout);
+        }
+        // an even number of passes: the sorted data is back in keys_a / idx_a; keep the names used below
+        std::swap(keys_a, keys_b);
+        std::swap(idx_a, idx_b);
     }
     const unsigned long long* keys = keys_b;
     const int* sorted = idx_b;  // the first n_rest entries are the tree's objects in Morton order
