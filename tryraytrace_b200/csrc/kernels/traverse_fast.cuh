@@ -270,39 +270,49 @@ struct NodeData {
 // different nodes spread over the banks), the rest sit in global memory 128 bytes apart.  Both
 // are read through ONE generic-address code path: a warp whose lanes are split between the two
 // spaces issues the seven loads once, not twice.
-template <bool GENERIC>
+// 256-bit read-only global load (sm_100: LDG.E.256): two adjacent float4 in one request
+TRT_DEV void ldg256(const unsigned char* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+TRT_DEV float4 sel4(bool take_b, const float4 a, const float4 b) {
+    return make_float4(take_b ? b.x : a.x, take_b ? b.y : a.y, take_b ? b.z : a.z, take_b ? b.w : a.w);
+}
+
+// WIDE = false: the generic path above (scenes whose tree top fits the staged / cached part).
+// WIDE = true: for trees far larger than the caches the traversal is bound by the number of L1
+// requests, seven scattered 16-byte loads per lane per node step; here the lo/hi plane vectors of
+// an axis (adjacent in the node) come in ONE 256-bit load and the near/far choice is made on the
+// registers -- four requests per node step instead of seven, nothing staged in shared memory.
+template <bool WIDE>
 TRT_DEV void load_node(NodeData& n, const unsigned char* s_nodes, int k_smem, const float4* g_nodes, int node, int nxo,
                        int nyo, int nzo) {
-    const bool staged = node < k_smem;
-    if (GENERIC) {
-        const unsigned char* b = staged ? s_nodes + (size_t)node * kSmemNodeStride
-                                        : reinterpret_cast<const unsigned char*>(g_nodes) + (size_t)node * 128;
-        n.nx = *reinterpret_cast<const float4*>(b + nxo);
-        n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
-        n.ny = *reinterpret_cast<const float4*>(b + nyo);
-        n.fy = *reinterpret_cast<const float4*>(b + (nyo ^ 16));
-        n.nz = *reinterpret_cast<const float4*>(b + nzo);
-        n.fz = *reinterpret_cast<const float4*>(b + (nzo ^ 16));
-        n.ch = *reinterpret_cast<const int4*>(b + 96);
-    } else if (staged) {
-        const unsigned char* b = s_nodes + node * kSmemNodeStride;
-        n.nx = *reinterpret_cast<const float4*>(b + nxo);
-        n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
-        n.ny = *reinterpret_cast<const float4*>(b + nyo);
-        n.fy = *reinterpret_cast<const float4*>(b + (nyo ^ 16));
-        n.nz = *reinterpret_cast<const float4*>(b + nzo);
-        n.fz = *reinterpret_cast<const float4*>(b + (nzo ^ 16));
-        n.ch = *reinterpret_cast<const int4*>(b + 96);
-    } else {
+    if (WIDE) {
         const unsigned char* b = reinterpret_cast<const unsigned char*>(g_nodes) + (size_t)node * 128;
-        n.nx = __ldg(reinterpret_cast<const float4*>(b + nxo));
-        n.fx = __ldg(reinterpret_cast<const float4*>(b + (nxo ^ 16)));
-        n.ny = __ldg(reinterpret_cast<const float4*>(b + nyo));
-        n.fy = __ldg(reinterpret_cast<const float4*>(b + (nyo ^ 16)));
-        n.nz = __ldg(reinterpret_cast<const float4*>(b + nzo));
-        n.fz = __ldg(reinterpret_cast<const float4*>(b + (nzo ^ 16)));
+        float4 lo, hi;
+        ldg256(b, lo, hi);
+        n.nx = sel4(nxo != 0, lo, hi);
+        n.fx = sel4(nxo != 0, hi, lo);
+        ldg256(b + 32, lo, hi);
+        n.ny = sel4(nyo != 32, lo, hi);
+        n.fy = sel4(nyo != 32, hi, lo);
+        ldg256(b + 64, lo, hi);
+        n.nz = sel4(nzo != 64, lo, hi);
+        n.fz = sel4(nzo != 64, hi, lo);
         n.ch = __ldg(reinterpret_cast<const int4*>(b + 96));
+        return;
     }
+    const bool staged = node < k_smem;
+    const unsigned char* b = staged ? s_nodes + (size_t)node * kSmemNodeStride
+                                    : reinterpret_cast<const unsigned char*>(g_nodes) + (size_t)node * 128;
+    n.nx = *reinterpret_cast<const float4*>(b + nxo);
+    n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
+    n.ny = *reinterpret_cast<const float4*>(b + nyo);
+    n.fy = *reinterpret_cast<const float4*>(b + (nyo ^ 16));
+    n.nz = *reinterpret_cast<const float4*>(b + nzo);
+    n.fz = *reinterpret_cast<const float4*>(b + (nzo ^ 16));
+    n.ch = *reinterpret_cast<const int4*>(b + 96);
 }
 
 // ---- closest hit -------------------------------------------------------------------------------
@@ -410,7 +420,7 @@ TRT_DEV bool closest_node_work(const ClosestRay& s, uint32_t base) {
     return s.cur != kWideEmptyRef || s.np != base || s.nspill > 0;
 }
 
-template <uint32_t E, int S, bool COUNT>
+template <uint32_t E, int S, bool COUNT, bool WIDE>
 TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ClosestRay& s,
                                uint32_t base, uint2* spill, WideCounts* wc) {
     const uint32_t ttop = base + (S - 1) * E;
@@ -442,7 +452,7 @@ TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const S
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node<true>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    load_node<WIDE>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
     // slab intervals of the four children, packed two per instruction
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
@@ -598,7 +608,7 @@ TRT_DEV bool shadow_node_work(const ShadowRay& s, uint32_t base) {
     return !s.occluded && (s.np != base || s.nspill > 0);
 }
 
-template <uint32_t E, int S, bool COUNT>
+template <uint32_t E, int S, bool COUNT, bool WIDE>
 TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const SceneDev& sc, ShadowRay& s,
                               uint32_t base, uint32_t* spill, WideCounts* wc) {
     const uint32_t ttop = base + (S - 1) * E;
@@ -619,7 +629,7 @@ TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const Sc
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node<true>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    load_node<WIDE>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
     const float4 az = plane_t(n.nz, s.o.z, s.inv.z), bz = plane_t(n.fz, s.o.z, s.inv.z);

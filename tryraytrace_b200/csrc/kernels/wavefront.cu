@@ -464,7 +464,7 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
     }
 }
 
-template <int THREADS, bool COUNT>
+template <int THREADS, bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
               int refill_below, Phases ph) {
@@ -561,7 +561,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         // 3. node phase: up to `node_iters` node steps, while enough lanes still have node work
 #pragma unroll 1
         for (int it = 0; it < ph.node_iters; it++) {
-            closest_node_step<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
+            closest_node_step<E, S, COUNT, WIDE>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, closest_node_work(st, stk_base) && closest_has_room<E, S>(st));
             if (__popc(m) < ph.node_min) break;
         }
@@ -588,7 +588,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     }
 }
 
-template <int THREADS, bool COUNT>
+template <int THREADS, bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
               int refill_below, Phases ph) {
@@ -680,7 +680,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         }
 #pragma unroll 1
         for (int it = 0; it < ph.node_iters; it++) {
-            shadow_node_step<E, S, COUNT>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
+            shadow_node_step<E, S, COUNT, WIDE>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, shadow_node_work(st, stk_base) && shadow_has_room<E, S>(st));
             if (__popc(m) < ph.node_min) break;
         }
@@ -854,15 +854,25 @@ size_t fast_smem_bytes(int k_smem, bool shadow) {
 template <int THREADS, bool COUNT>
 void launch_extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                         const LaunchDims& dims, cudaStream_t s) {
+    if (dims.wide_loads && THREADS == 768) {  // big scenes: 256-bit node loads, nothing staged
+        k_extend_fast<768, COUNT, true><<<dims.sms, 768, fast_smem_bytes<768>(0, false), s>>>(
+            pool, sc, top, ctl, 0, dims.refill_below, dims.closest_phases);
+        return;
+    }
     const int k = min(dims.smem_nodes, sc.n_wide_nodes);
-    k_extend_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, false), s>>>(
+    k_extend_fast<THREADS, COUNT, false><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, false), s>>>(
         pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases);
 }
 template <int THREADS, bool COUNT>
 void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                         const LaunchDims& dims, cudaStream_t s) {
+    if (dims.wide_loads && THREADS == 768) {
+        k_shadow_fast<768, COUNT, true><<<dims.sms, 768, fast_smem_bytes<768>(0, true), s>>>(
+            pool, sc, top, ctl, 0, dims.refill_below, dims.shadow_phases);
+        return;
+    }
     const int k = min(dims.smem_nodes, sc.n_wide_nodes);
-    k_shadow_fast<THREADS, COUNT><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, true), s>>>(
+    k_shadow_fast<THREADS, COUNT, false><<<dims.sms, THREADS, fast_smem_bytes<THREADS>(k, true), s>>>(
         pool, sc, top, ctl, k, dims.refill_below, dims.shadow_phases);
 }
 
@@ -895,18 +905,22 @@ int opt_in_smem(K kernel) {
 // ---- launchers -------------------------------------------------------------------------------
 int wf_configure() {
     int rc = 0;
-    rc |= opt_in_smem(k_extend_fast<512, false>);
-    rc |= opt_in_smem(k_extend_fast<512, true>);
-    rc |= opt_in_smem(k_extend_fast<768, false>);
-    rc |= opt_in_smem(k_extend_fast<768, true>);
-    rc |= opt_in_smem(k_extend_fast<1024, false>);
-    rc |= opt_in_smem(k_extend_fast<1024, true>);
-    rc |= opt_in_smem(k_shadow_fast<512, false>);
-    rc |= opt_in_smem(k_shadow_fast<512, true>);
-    rc |= opt_in_smem(k_shadow_fast<768, false>);
-    rc |= opt_in_smem(k_shadow_fast<768, true>);
-    rc |= opt_in_smem(k_shadow_fast<1024, false>);
-    rc |= opt_in_smem(k_shadow_fast<1024, true>);
+    rc |= opt_in_smem(k_extend_fast<512, false, false>);
+    rc |= opt_in_smem(k_extend_fast<512, true, false>);
+    rc |= opt_in_smem(k_extend_fast<768, false, false>);
+    rc |= opt_in_smem(k_extend_fast<768, true, false>);
+    rc |= opt_in_smem(k_extend_fast<1024, false, false>);
+    rc |= opt_in_smem(k_extend_fast<1024, true, false>);
+    rc |= opt_in_smem(k_shadow_fast<512, false, false>);
+    rc |= opt_in_smem(k_shadow_fast<512, true, false>);
+    rc |= opt_in_smem(k_shadow_fast<768, false, false>);
+    rc |= opt_in_smem(k_shadow_fast<768, true, false>);
+    rc |= opt_in_smem(k_shadow_fast<1024, false, false>);
+    rc |= opt_in_smem(k_shadow_fast<1024, true, false>);
+    rc |= opt_in_smem(k_extend_fast<768, false, true>);
+    rc |= opt_in_smem(k_extend_fast<768, true, true>);
+    rc |= opt_in_smem(k_shadow_fast<768, false, true>);
+    rc |= opt_in_smem(k_shadow_fast<768, true, true>);
     return rc;
 }
 

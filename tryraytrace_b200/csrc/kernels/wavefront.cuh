@@ -80,6 +80,7 @@ struct LaunchDims {
     int sms;
     int fast_threads;   // threads of the persistent traversal CTAs (one CTA per SM): 512, 768 or 1024
     int smem_nodes;     // wide nodes staged into shared memory per CTA (top of the tree)
+    bool wide_loads;    // big scenes: 256-bit node loads instead of staging (traverse_fast.cuh load_node<true>)
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
     int shade_block;    // threads per shade CTA (64 .. 512; the pool capacity is a multiple of 512): larger CTAs, fewer
                         // free-list atomics and barriers waiting on them
