@@ -17,7 +17,7 @@ CU_OBJS   := $(OBJDIR)/wavefront.o $(OBJDIR)/bvh_build.o $(OBJDIR)/trt_capi.o
 .PHONY: all lib oracle assets clean
 all: lib oracle assets
 
-lib: $(LIBDIR)/libtrt_b200.so
+lib: $(LIBDIR)/libtrt_b200.so $(LIBDIR)/libtrt_b200_mgpu.so
 
 $(OBJDIR)/%.o: $(CSRC)/host/%.cpp $(wildcard include/*.h) $(wildcard $(CSRC)/host/*.h)
 	@mkdir -p $(OBJDIR)
@@ -38,6 +38,10 @@ $(OBJDIR)/trt_capi.o: $(CSRC)/capi/trt_capi.cu $(wildcard $(CSRC)/kernels/*.cuh)
 $(LIBDIR)/libtrt_b200.so: $(HOST_OBJS) $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) -shared $(ARCH) -o $@ $^ -Xcompiler -fopenmp -Xlinker -Bsymbolic -lgomp
+
+# single-process multi-GPU layer (include/trt_mgpu.h): its own library, because it links NCCL
+$(LIBDIR)/libtrt_b200_mgpu.so: $(CSRC)/capi/trt_mgpu.cpp include/trt_mgpu.h include/trt_capi.h $(LIBDIR)/libtrt_b200.so
+	$(CXX) -O2 -fPIC -std=c++17 $(INC) -Wall -shared -o $@ $< -L$(LIBDIR) -ltrt_b200 -L/usr/local/cuda/lib64 -lcudart -lnccl -lpthread -Wl,-rpath,'$$ORIGIN'
 
 oracle:
 	$(MAKE) -C oracle all
