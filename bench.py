@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp", type=int, default=SPP)
-    ap.add_argument("--pool", type=int, default=8 << 20, help="wavefront pool size (paths in flight)")
+    ap.add_argument("--pool", type=int, default=0, help="wavefront pool size (paths in flight); 0 = the library's rule (a quarter of the step's samples, 256 Ki .. 32 Mi)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -188,7 +188,8 @@ def main():
     config = {"workload": workload, "spp_per_step": args.spp, "width": w, "height": h,
               "sharding": f"sample index, stride {world}, one all-reduce of the accumulation buffer per step" if world > 1
               else "single GPU", "l2": "no explicit L2 flush: each step streams the wavefront pool "
-              "(1.1 GB of path state) and the 33 MB accumulation buffer, both larger than or comparable to the 126 MB L2"}
+              "(132 B of path state per slot: 4.4 GB at the 32 Mi slots the library picks for this step) and the 33 MB "
+              "accumulation buffer, both larger than or comparable to the 126 MB L2"}
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":
@@ -402,7 +403,7 @@ def main():
                     "api": "trt_render_to_host (scene resident on the device; camera/options from host, "
                            "accumulation buffer cleared on device, result copied to pinned host memory)"},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "pool_paths": args.pool}
+            "pool_paths": args.pool if args.pool else "auto"}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

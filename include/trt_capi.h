@@ -46,7 +46,7 @@ typedef struct {
     int rr_threshold;
     int seed_base;
     int traversal;      /* TRT_TRAVERSE_* */
-    int pool_paths;     /* wavefront pool size (paths in flight); 0 = sized to the job (256 Ki .. 16 Mi) */
+    int pool_paths;     /* wavefront pool size (paths in flight); 0 = sized to the job (256 Ki .. 32 Mi) */
     int count_rays;     /* 1 = also count node fetches / triangle tests (small cost); ray
                            and sample counts are always maintained */
     int time_kernels;   /* 1 = record CUDA events at every kernel boundary (see trt_kernel_times);

@@ -47,6 +47,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr int kFrameChunkDefault = 256;  // frames per wavefront job (bounds the column-vector table); TRT_FRAME_CHUNK overrides
 constexpr int kBatchIterations = 16;  // iterations issued between completion polls
+constexpr int kTailBatchIterations = 4;  // ... once the job is within reach of its drain phase: the poll drives the grid sizes there
 constexpr int kWideStackEntries = 128;  // kernels/traverse_fast.cuh kSpillEntries
 constexpr int kAutoDeviceBuildAbove = 1 << 18;  // TRT_BUILD_AUTO: objects above which the device builder is used
 
@@ -377,17 +378,18 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_rng_tables(c, w, h)) return rc;
     int kFrameChunk = kFrameChunkDefault;
     if (const char* e = getenv("TRT_FRAME_CHUNK")) kFrameChunk = std::max(1, std::min(1024, atoi(e)));
-    // pool_paths = 0: size the pool to the job -- a sixteenth of the samples of one job (at most
-    // kFrameChunk frames) in flight, between 256 Ki and 16 Mi slots (B200 sweeps with drain compaction and
-    // overlapped regeneration: 512 Ki..1 Mi for the 4.9 M samples of C1, 8 Mi for C2 at 64 spp, 16 Mi at 4K)
+    // pool_paths = 0: size the pool to the job -- a quarter of the samples of one job (at most
+    // kFrameChunk frames) in flight, between 256 Ki and 32 Mi slots.  B200 sweeps with drain compaction,
+    // overlapped regeneration and poll-driven grids: every iteration has a fixed cost (launch gaps, the
+    // start-up and tail of the persistent kernels), so fewer, larger iterations win until the drain phase
+    // dominates -- C1 (4.9 M samples) 0.53 / 0.46 / 0.42 ms/spp at 512 Ki / 1 Mi / 2 Mi, C2 at 64 spp
+    // (133 M samples) 3.01 / 2.82 / 2.73 / 2.72 at 4 / 8 / 16 / 32 Mi, C4 9.96 / 9.81 at 16 / 32 Mi
     int pool_paths = o.pool_paths;
     if (pool_paths == 0) {
         const unsigned long long want =
-            (unsigned long long)w * h * (unsigned long long)std::min(n_frames, kFrameChunk) / 16;
+            (unsigned long long)w * h * (unsigned long long)std::min(n_frames, kFrameChunk) / 4;
         pool_paths = 256 << 10;
-        while (pool_paths < (16 << 20) && (unsigned long long)pool_paths < want) pool_paths <<= 1;
-        // ... but at least 1 Mi when the job has that many samples (C1: 1 Mi beats 512 Ki by 7 %)
-        while (pool_paths < (1 << 20) && (unsigned long long)pool_paths < want * 16) pool_paths <<= 1;
+        while (pool_paths < (32 << 20) && (unsigned long long)pool_paths < want) pool_paths <<= 1;
     }
     if (int rc = ensure_pool(c, pool_paths)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
@@ -400,7 +402,6 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     bool compact = true;
     if (const char* e = getenv("TRT_COMPACT")) compact = atoi(e) != 0;
     const LaunchDims dims = launch_dims(c);
-    const int kpi = wf_kernels_per_iteration(o.traversal);
     CU(cudaEventRecord(c->ev_begin, c->stream));
     const unsigned long long pixels = (unsigned long long)w * h;
     for (int f0 = 0; f0 < n_frames; f0 += kFrameChunk) {
@@ -413,12 +414,16 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         wf_begin_job(c->d_ctl, pixels * nf, c->pool_cap, c->stream);
         c->launches += 3;
         if (st.overlap) CU(cudaEventRecord(st.fork, c->stream));
+        st.visit_cap = c->pool_cap;
+        st.samples_left = true;
         // Issue batches of iterations, staying one batch ahead of the completion poll.
         // the compaction kernels ride along once the job can reach its drain phase within the batches
         // in flight (the poll is up to two batches old; an iteration starts about capacity / 6 samples)
         bool near_drain = pixels * nf <= 8ull * (unsigned long long)c->pool_cap;
-        auto issue = [&](int slot) -> int {
-            for (int i = 0; i < kBatchIterations; i++) {
+        // ... and with the short batches of that stretch the poll is at most 8 iterations old
+        bool compact_near = pixels * nf <= 2ull * (unsigned long long)c->pool_cap;
+        auto issue = [&](int slot, int n_iter) -> int {
+            for (int i = 0; i < n_iter; i++) {
                 cudaEvent_t* marks = nullptr;
                 if (o.time_kernels) {
                     while (c->marks.size() < c->marks_used + 6) {
@@ -429,31 +434,42 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
                     marks = c->marks.data() + c->marks_used;
                     c->marks_used += 6;
                 }
-                wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, c->top, job, o.traversal, o.count_rays != 0, dims,
-                             st, marks, near_drain && compact ? c->d_compact : nullptr);
+                c->launches += (unsigned long long)wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, c->top, job, o.traversal,
+                                                                o.count_rays != 0, dims, st, marks,
+                                                                compact_near && compact ? c->d_compact : nullptr);
             }
-            c->launches += (unsigned long long)kBatchIterations * (kpi + (near_drain && compact ? 3 : 0));
             CU(cudaMemcpyAsync(&c->h_ctl[slot], c->d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaEventRecord(c->ev_poll[slot], c->stream));
             return 0;
         };
         // every iteration advances each live path by one vertex, so the job needs at most
         // (samples / pool + 1) * (max_depth + 2) iterations; anything beyond that is a bug
-        const unsigned long long max_batches =
-            ((pixels * nf) / (unsigned long long)c->pool_cap + 2) * (unsigned long long)(o.max_depth + 2) /
-                kBatchIterations + 8;
-        unsigned long long b = 0;
-        if (int rc = issue(0)) return rc;
+        const unsigned long long max_iterations =
+            ((pixels * nf) / (unsigned long long)c->pool_cap + 2) * (unsigned long long)(o.max_depth + 2) +
+            8 * kBatchIterations;
+        unsigned long long issued = 0, b = 0;
+        int batch = near_drain ? kTailBatchIterations : kBatchIterations;
+        if (int rc = issue(0, batch)) return rc;
+        issued += (unsigned long long)batch;
         for (;;) {
-            if (int rc = issue((int)((b + 1) & 1))) return rc;
+            if (int rc = issue((int)((b + 1) & 1), batch)) return rc;
+            issued += (unsigned long long)batch;
             CU(cudaEventSynchronize(c->ev_poll[b & 1]));
             const Control& hc = c->h_ctl[b & 1];
             if (hc.alive == 0 && hc.next_sample == hc.total_samples) break;
             if (hc.total_samples - hc.next_sample <= 8ull * (unsigned long long)c->pool_cap) near_drain = true;
-            if (++b > max_batches) {
+            if (hc.total_samples - hc.next_sample <= 2ull * (unsigned long long)c->pool_cap) compact_near = true;
+            // what the poll says about the rest of the job: the shade grid follows the compacted bound,
+            // regeneration stops with the last sample; towards the drain phase the batches are short, so that
+            // the bound is fresh and few iterations are queued behind the last live path
+            st.visit_cap = std::min(st.visit_cap, hc.active_cap);
+            if (hc.next_sample == hc.total_samples) st.samples_left = false;
+            if (near_drain) batch = kTailBatchIterations;
+            b++;
+            if (issued > max_iterations) {
                 cudaStreamSynchronize(c->stream);
-                return fail(TRT_ERR_STATE, "wavefront did not drain after %llu batches (alive=%d, next=%llu of %llu)",
-                            b, hc.alive, hc.next_sample, hc.total_samples);
+                return fail(TRT_ERR_STATE, "wavefront did not drain after %llu iterations (alive=%d, next=%llu of %llu)",
+                            issued, hc.alive, hc.next_sample, hc.total_samples);
             }
         }
     }
@@ -864,6 +880,9 @@ int trt_kernel_times_get(trt_ctx* c, trt_kernel_times* out) {
     CU(cudaStreamSynchronize(c->stream));
     trt_kernel_times t;
     memset(&t, 0, sizeof(t));
+    // TRT_ITER_LOG=<file>: one line per timed iteration (tuning aid; needs time_kernels = 1)
+    FILE* log = nullptr;
+    if (const char* e = getenv("TRT_ITER_LOG")) if (c->marks_mask == 0x3f) log = fopen(e, "w");
     for (size_t i = 0; i + 6 <= c->marks_used; i += 6) {  // marks: [0] prepare+regenerate [1], [2] extend [3] shade [4] shadow [5]
         float ms[4] = {0.f, 0.f, 0.f, 0.f};
         if (c->marks_mask == 0x3f) {
@@ -877,7 +896,13 @@ int trt_kernel_times_get(trt_ctx* c, trt_kernel_times* out) {
         t.shade_ms += ms[2];
         t.shadow_ms += ms[3];
         t.iterations++;
+        if (log) {
+            float whole = 0.f;  // start of this iteration's extend to the start of the next one's
+            if (i + 12 <= c->marks_used) cudaEventElapsedTime(&whole, c->marks[i + 2], c->marks[i + 8]);
+            fprintf(log, "%d %.4f %.4f %.4f %.4f %.4f\n", t.iterations - 1, ms[0], ms[1], ms[2], ms[3], whole);
+        }
     }
+    if (log) fclose(log);
     *out = t;
     return 0;
 }

@@ -102,22 +102,30 @@ __global__ void k_reset_cursors(Control* ctl) {
 // slots beyond the new bound are moved into dead slots below it and active_cap shrinks, so the
 // kernels of the remaining iterations visit a dense prefix of the pool.
 // scan: A = live slots in [new_cap, active_cap), B = dead slots in [0, new_cap)   (|B| >= |A|)
-__global__ void __launch_bounds__(kBlock) k_compact_scan(PoolView pool, Control* ctl, int* list_a, int* list_b) {
+__global__ void __launch_bounds__(1024) k_compact_scan(PoolView pool, Control* ctl, int* list_a, int* list_b) {
     if (!ctl->compact_go) return;
+    // list positions: shared-memory atomics within the block, one global atomic per block, list and round
+    // (a global atomic per warp is a quarter of a million adds on two addresses: 0.4 ms at 8 Mi slots)
+    __shared__ int count[2], base[2];
     const int cap = ctl->active_cap, new_cap = ctl->compact_new_cap;
     const unsigned lane = threadIdx.x & 31u;
-    for (int base = blockIdx.x * blockDim.x; base < cap; base += gridDim.x * blockDim.x) {
-        const int slot = base + threadIdx.x;
+    for (int first = blockIdx.x * blockDim.x; first < cap; first += gridDim.x * blockDim.x) {
+        if (threadIdx.x < 2) count[threadIdx.x] = 0;
+        __syncthreads();
+        const int slot = first + threadIdx.x;
         const bool live = slot < cap && (f2i(pool.ray_d[slot].w) & 0xff) != SLOT_DEAD;
         const bool to_a = live && slot >= new_cap, to_b = !live && slot < new_cap;
         const unsigned ma = __ballot_sync(0xffffffffu, to_a), mb = __ballot_sync(0xffffffffu, to_b);
         int ba = 0, bb = 0;
         if (lane == 0) {
-            if (ma) ba = atomicAdd(&ctl->compact_a, __popc(ma));
-            if (mb) bb = atomicAdd(&ctl->compact_b, __popc(mb));
+            if (ma) ba = atomicAdd(&count[0], __popc(ma));
+            if (mb) bb = atomicAdd(&count[1], __popc(mb));
         }
-        ba = __shfl_sync(0xffffffffu, ba, 0);
-        bb = __shfl_sync(0xffffffffu, bb, 0);
+        __syncthreads();
+        if (threadIdx.x < 2) base[threadIdx.x] = count[threadIdx.x] ? atomicAdd(threadIdx.x ? &ctl->compact_b : &ctl->compact_a, count[threadIdx.x]) : 0;
+        __syncthreads();
+        ba = __shfl_sync(0xffffffffu, ba, 0) + base[0];
+        bb = __shfl_sync(0xffffffffu, bb, 0) + base[1];
         if (to_a) list_a[ba + __popc(ma & ((1u << lane) - 1u))] = slot;
         if (to_b) list_b[bb + __popc(mb & ((1u << lane) - 1u))] = slot;
     }
@@ -195,7 +203,7 @@ TRT_DEV Xorwow sample_rng(const JobParams& job, int f, int row, int col) {
 }
 
 // ---- regenerate: refill freed slots with the next camera samples ----------------------
-__global__ void __launch_bounds__(kBlock) k_regen(PoolView pool, const int* __restrict__ free_list,
+__global__ void __launch_bounds__(kBlock, 6) k_regen(PoolView pool, const int* __restrict__ free_list,
                                                   const Control* __restrict__ ctl, JobParams job) {
     const int n = ctl->n_regen;
     const unsigned long long base = ctl->regen_base;
@@ -957,70 +965,80 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
                                                             seed_base, n_frames, out);
 }
 
-int wf_kernels_per_iteration(int) { return 5; }
-
-// One iteration.  Side part: prepare -> [compact] -> regenerate.  Main part: extend -> shade -> shadow.
+// One iteration.  Side part: prepare -> regenerate.  Main part: [compact] -> extend -> shade -> shadow.
 // With st.overlap the side part of iteration i+1 runs on its own stream as soon as shade(i) is done,
 // i.e. concurrently with shadow(i): regenerate is a latency-bound stream of scattered stores
 // (about a sixth of the slots), the shadow kernel is issue bound and leaves room for one small
-// regenerate CTA per SM, so the refill disappears behind the traversal.  The two touch disjoint
-// state: regenerate writes slots that ended in shade(i) (their shadow flag is already cleared),
-// prepare leaves the shadow cursor alone.  Compaction moves slots the shadow kernel reads, so in the
-// drain phase (compact_lists set) the side part waits for shadow(i) instead.
+// regenerate CTA per SM, so most of the refill disappears behind the traversal.  The two touch
+// disjoint state: regenerate writes slots that ended in shade(i) (their shadow flag is already
+// cleared), prepare leaves the shadow cursor alone.  Compaction moves slots the shadow kernel reads,
+// so its kernels run on the main stream, behind shadow(i) and the join; prepare only lets it go in an
+// iteration that regenerates nothing, so the order of the two does not matter.
+// Once the job has no samples left (st.samples_left false) there is nothing to overlap and the whole
+// iteration is issued on the main stream.
 template <int MODE, bool COUNT>
-static void iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
-                           const JobParams& job, const LaunchDims& dims, const IterStreams& st, cudaEvent_t* marks,
-                           int* compact_lists) {
+static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+                          const JobParams& job, const LaunchDims& dims, const IterStreams& st, cudaEvent_t* marks,
+                          int* compact_lists) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
-    cudaStream_t s = st.main, side = st.overlap ? st.side : st.main;
+    const bool overlap = st.overlap && st.samples_left;
+    cudaStream_t s = st.main, side = overlap ? st.side : st.main;
+    int launched = 0;
     // marks[0..5]; st.mark_mask selects which of them are recorded
     auto mark = [&](int i, cudaStream_t on) { if (marks && ((st.mark_mask >> i) & 1)) cudaEventRecord(marks[i], on); };
-    if (st.overlap) cudaStreamWaitEvent(side, st.fork, 0);
+    if (overlap) cudaStreamWaitEvent(side, st.fork, 0);
     mark(0, side);
     k_prepare<<<1, 32, 0, side>>>(ctl, dims.compact_quarters);
-    if (compact_lists) {  // the host launches these only once the job is close to its drain phase
-        int* list_a = compact_lists;
-        int* list_b = compact_lists + pool.capacity / 2 + 512;
-        k_compact_scan<<<persistent, kBlock, 0, side>>>(pool, ctl, list_a, list_b);
-        k_compact_move<<<persistent, kBlock, 0, side>>>(pool, ctl, list_a, list_b);
-        k_compact_commit<<<1, 32, 0, side>>>(ctl);
+    launched++;
+    if (st.samples_left) {
+        // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
+        // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up;
+        // small CTAs so that one fits beside the persistent shadow CTA of an SM
+        const int kRegenBlock = dims.regen_block;
+        const int regen_full = (pool.capacity + kRegenBlock - 1) / kRegenBlock;
+        const int regen_blocks = min(regen_full, max(2 * persistent, regen_full / 4));
+        k_regen<<<regen_blocks, kRegenBlock, 0, side>>>(pool, free_list, ctl, job);
+        launched++;
     }
-    // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
-    // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up;
-    // small CTAs so that one fits beside the persistent shadow CTA of an SM
-    const int kRegenBlock = dims.regen_block;
-    const int regen_full = (pool.capacity + kRegenBlock - 1) / kRegenBlock;
-    const int regen_blocks = min(regen_full, max(2 * persistent, regen_full / 4));
-    k_regen<<<regen_blocks, kRegenBlock, 0, side>>>(pool, free_list, ctl, job);
     mark(1, side);
-    if (st.overlap) {
+    if (overlap) {
         cudaEventRecord(st.join, side);
         cudaStreamWaitEvent(s, st.join, 0);
+    }
+    const int visit = min(pool.capacity, st.visit_cap);
+    if (compact_lists && visit > kCompactMinCap) {  // the host launches these only once the job is close to its drain phase
+        int* list_a = compact_lists;
+        int* list_b = compact_lists + pool.capacity / 2 + 512;
+        k_compact_scan<<<dims.sms * 2, 1024, 0, s>>>(pool, ctl, list_a, list_b);
+        k_compact_move<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b);
+        k_compact_commit<<<1, 32, 0, s>>>(ctl);
+        launched += 3;
     }
     mark(2, s);
     if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(3, s);
-    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<pool.capacity / dims.shade_block, dims.shade_block, 0, s>>>(pool, free_list, ctl, sc, job);
+    // blocks beyond active_cap return at once, but 16 Ki of them still cost 0.1 ms: size the grid by the bound
+    const int shade_blocks = (visit + dims.shade_block - 1) / dims.shade_block;
+    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<shade_blocks, dims.shade_block, 0, s>>>(pool, free_list, ctl, sc, job);
     mark(4, s);
-    if (st.overlap && !compact_lists) cudaEventRecord(st.fork, s);  // the next side part may start now
+    if (st.overlap) cudaEventRecord(st.fork, s);  // the next side part may start now
     if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(5, s);
-    if (st.overlap && compact_lists) cudaEventRecord(st.fork, s);
+    return launched + 3;
 }
 
-void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
-                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, const IterStreams& st,
-                  cudaEvent_t* marks, int* compact_lists) {
+int wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+                 const JobParams& job, int traversal, bool count, const LaunchDims& dims, const IterStreams& st,
+                 cudaEvent_t* marks, int* compact_lists) {
     if (traversal == TRT_TRAVERSE_REF) {
-        if (count) iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
-        else iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
-    } else {
-        if (count) iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
-        else iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
+        if (count) return iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
+        return iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
     }
+    if (count) return iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
+    return iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
 }
 
 void wf_trace_primary(const SceneDev& sc, const JobParams& job, int, int traversal, int* d_id, float* d_t,

@@ -109,15 +109,18 @@ struct IterStreams {
     cudaEvent_t fork, join;
     bool overlap;
     int mark_mask = 0x3f;  // which of the six timing marks of an iteration are recorded
+    // what the host knows from its last completion poll (stale values are safe: active_cap only shrinks
+    // and next_sample only grows within a job)
+    int visit_cap = 0x7fffffff;  // upper bound of Control::active_cap: sizes the shade grid
+    bool samples_left = true;    // false: the job has handed out its last sample, nothing to regenerate
 };
-// one wavefront iteration on the streams of `st`
+// one wavefront iteration on the streams of `st`; returns the number of kernels it launched
 // `marks`, when not null, receives six events: [0] prepare+regenerate [1]  and  [2] extend [3] shade [4] shadow [5]
-void wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
-                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, const IterStreams& st,
-                  cudaEvent_t* marks = nullptr, int* compact_lists = nullptr);
+int wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+                 const JobParams& job, int traversal, bool count, const LaunchDims& dims, const IterStreams& st,
+                 cudaEvent_t* marks = nullptr, int* compact_lists = nullptr);
 // one-time opt-in to large dynamic shared memory for the persistent kernels
 int wf_configure();
-int wf_kernels_per_iteration(int traversal);
 
 // Parity / test entry points.  In FAST mode they run the production persistent kernels over a
 // scratch pool (`scratch`, capacity >= n rounded up to 256; `ctl` is the context's control block).
