@@ -138,15 +138,19 @@ __global__ void __launch_bounds__(kBlock) k_compact_move(PoolView pool, const Co
     const int n = ctl->compact_a;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int src = list_a[i], dst = list_b[i];
-        pool.ray_o[dst] = pool.ray_o[src];
-        pool.ray_d[dst] = pool.ray_d[src];
-        pool.thr[dst] = pool.thr[src];
-        pool.rad[dst] = pool.rad[src];
-        pool.pend[dst] = pool.pend[src];
-        pool.sh_d[dst] = pool.sh_d[src];
-        pool.rng_a[dst] = pool.rng_a[src];
-        pool.rng_b[dst] = pool.rng_b[src];
-        pool.hit[dst] = pool.hit[src];
+        // `hit` and `sh_d` stay behind: compaction runs between shadow(i) and extend(i+1), so the shadow ray
+        // has been traced (dst is a dead slot, its flag is already clear; src is never visited again) and the
+        // hit record is rewritten by extend before shade reads it
+        const float4 o = pool.ray_o[src], d = pool.ray_d[src], t = pool.thr[src], r = pool.rad[src], pe = pool.pend[src];
+        const uint4 ra = pool.rng_a[src];
+        const uint2 rb = pool.rng_b[src];
+        pool.ray_o[dst] = o;
+        pool.ray_d[dst] = d;
+        pool.thr[dst] = t;
+        pool.rad[dst] = r;
+        pool.pend[dst] = pe;
+        pool.rng_a[dst] = ra;
+        pool.rng_b[dst] = rb;
     }
 }
 
