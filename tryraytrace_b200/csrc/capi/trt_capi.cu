@@ -417,10 +417,11 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         st.visit_cap = c->pool_cap;
         st.samples_left = true;
         // Issue batches of iterations, staying one batch ahead of the completion poll.
-        // the compaction kernels ride along once the job can reach its drain phase within the batches
-        // in flight (the poll is up to two batches old; an iteration starts about capacity / 6 samples)
+        // near_drain: the job can reach its drain phase within the batches in flight (the poll is up to two
+        // batches old; an iteration starts about capacity / 6 samples) -- from here on the batches are short.
+        // compact_near: the same with the short batches (poll at most 8 iterations old) -- from here on the
+        // compaction kernels ride along; late by an iteration or two only costs time, never correctness
         bool near_drain = pixels * nf <= 8ull * (unsigned long long)c->pool_cap;
-        // ... and with the short batches of that stretch the poll is at most 8 iterations old
         bool compact_near = pixels * nf <= 2ull * (unsigned long long)c->pool_cap;
         auto issue = [&](int slot, int n_iter) -> int {
             for (int i = 0; i < n_iter; i++) {
