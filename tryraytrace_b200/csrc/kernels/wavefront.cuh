@@ -2,9 +2,9 @@
 // launch interface implemented in wavefront.cu.
 //
 // A fixed pool of P path slots lives in HBM.  Every iteration runs
-//     prepare -> [compact] -> regenerate -> extend (closest hit) -> shade -> shadow (any hit)
-// over the pool (prepare/regenerate of the next iteration on a side stream, behind the shadow
-// kernel).  Paths that end are accumulated into the caller's buffer and their slots
+//     prepare -> regenerate -> [compact] -> extend (closest hit) -> shade -> shadow (any hit)
+// over the pool (prepare/regenerate of the next iteration on a side stream, beside the shadow
+// kernel; compaction, drain phase only, on the main stream behind it).  Paths that end are accumulated into the caller's buffer and their slots
 // go to a free list; `regenerate` refills those slots with the next camera samples of the
 // job, so the extend kernel always sees a full pool until the job drains; in the drain phase the
 // live slots are compacted into a prefix of the pool (active_cap).  Shadow rays are
