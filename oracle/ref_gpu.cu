@@ -95,6 +95,28 @@ __global__ void k_full_counts(Vec* accum, int width, int height, int seed, ptr::
     atomicAdd(&totals[4], c.tris_tested);
 }
 
+// Arbitrary rays (8 floats each: o.xyz, d.xyz, t_max, unused) against the uploaded scene.
+//   closest: the restatement of renderer.cu:371-425 (ptr::closest_hit; its ids are checked against
+//            the unmodified kernel's ID plane in every parity test)            -> id, d_min
+//   shadow : the reference's OWN, unmodified __device__ function trace_shadow (renderer.cu:273-314),
+//            called on the device arrays init_scene_data uploaded                -> 0/1
+__global__ void k_trace_rays(const float* rays, int n, int shadow, ptr::SceneView sc, LinearBVHNode* nodes,
+                             Object* objs, int* out_id, float* out_t, int* out_occ) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = rays + (size_t)i * 8;
+    if (shadow) {
+        Vec o = make_vec(p[0], p[1], p[2]), d = make_vec(p[3], p[4], p[5]);
+        out_occ[i] = trace_shadow(o, d, p[6], nodes, objs) ? 1 : 0;
+    } else {
+        ptr::Counters c = {0, 0, 0, 0, 0};
+        float t;
+        int id = ptr::closest_hit(sc, ptr::mk(p[0], p[1], p[2]), ptr::mk(p[3], p[4], p[5]), &t, &c);
+        if (out_id) out_id[i] = id;
+        if (out_t) out_t[i] = t;
+    }
+}
+
 // host copies of what was last handed to init_scene_data (for the ID-emission trick)
 std::vector<Object> g_objects;
 std::vector<LinearBVHNode> g_nodes;
@@ -314,6 +336,15 @@ int ref_full_counts(void* d_accum, int w, int h, int seed_base, int first_frame,
         k_full_counts<<<blocks, threads>>>((Vec*)d_accum, w, h, seed_base + first_frame + f, c, scene_view(), k,
                                            g_totals);
     cudaMemcpy(totals_out, g_totals, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return cuda_ok();
+}
+
+// Arbitrary-ray oracle (see k_trace_rays).  d_rays / outputs are DEVICE pointers.
+int ref_trace_rays(const float* d_rays, int n, int shadow, int* d_id, float* d_t, int* d_occ) {
+    if (n <= 0) return 0;
+    if (shadow ? !d_occ : !d_id) return -1;
+    k_trace_rays<<<(n + 255) / 256, 256>>>(d_rays, n, shadow, scene_view(), d_bvh_nodes, d_objects_ptr, d_id, d_t, d_occ);
+    cudaDeviceSynchronize();
     return cuda_ok();
 }
 

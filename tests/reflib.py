@@ -130,6 +130,13 @@ def primary_counts(w, h, frame_seed, cam, d_id=None, d_t=None, d_ray=None, d_fet
     assert rc == 0
 
 
+def trace_rays(d_rays, n, shadow, d_id=None, d_t=None, d_occ=None):
+    """Arbitrary rays through the oracle: closest hit = restatement of reference renderer.cu:371-425,
+    shadow = the reference's own unmodified trace_shadow (:273-314)."""
+    rc = ref().ref_trace_rays(_dp(d_rays), int(n), int(shadow), _dp(d_id), _dp(d_t), _dp(d_occ))
+    assert rc == 0, f"ref_trace_rays failed ({rc})"
+
+
 def full_counts(d_accum, w, h, first, n, cam, max_depth=30, rr_threshold=3, seed_base=1984):
     tot = np.zeros(5, dtype=np.uint64)
     rc = ref().ref_full_counts(_dp(d_accum), w, h, seed_base, first, n, _p(cam), max_depth, rr_threshold, _p(tot))

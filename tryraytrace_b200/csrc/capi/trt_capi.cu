@@ -226,8 +226,8 @@ int ensure_col_vecs(trt_ctx* c, size_t entries) {
 // One allocation, carved into the SoA arrays of PoolView (+ the free list when asked for).
 int alloc_pool(int cap, bool with_free_list, void** mem, PoolView* pool, int** free_list) {
     const size_t n = (size_t)cap;
-    // 7 float4/uint4 arrays + hit (float2) + rng_b (uint2) + free list (int)
-    const size_t bytes = n * (7 * 16 + 2 * 8 + (with_free_list ? 4 : 0));
+    // 7 float4/uint4 arrays + hit (float2) + rng_b (uint2) + free list (int) + dead mask (1 bit per slot)
+    const size_t bytes = n * (7 * 16 + 2 * 8 + (with_free_list ? 4 : 0)) + (with_free_list ? n / 8 + 64 : 0);
     CU(cudaMalloc(mem, bytes));
     char* p = (char*)*mem;
     auto take = [&](size_t b) { void* r = p; p += b; return r; };
@@ -241,6 +241,7 @@ int alloc_pool(int cap, bool with_free_list, void** mem, PoolView* pool, int** f
     pool->hit = (float2*)take(n * 8);
     pool->rng_b = (uint2*)take(n * 8);
     if (free_list) *free_list = with_free_list ? (int*)take(n * 4) : nullptr;
+    pool->dead_mask = with_free_list ? (uint32_t*)take(n / 8 + 64) : nullptr;
     pool->capacity = cap;
     return 0;
 }
@@ -855,6 +856,19 @@ int trt_get_counters(trt_ctx* c, trt_counters* out) {
     out->tris_closest = hc.cnt_tris_closest;
     out->tree_closest = hc.cnt_tree_closest;
     out->tree_shadow = hc.cnt_tree_shadow;
+    if (getenv("TRT_TRAV_STATS")) {  // lane-utilisation statistics of the traversal kernels (count_rays renders)
+        const unsigned long long nodes_shadow = hc.cnt_nodes - hc.cnt_nodes_closest, tris_shadow = hc.cnt_tris - hc.cnt_tris_closest;
+        auto line = [&](const char* name, const unsigned long long* d, unsigned long long rays, unsigned long long tree,
+                        unsigned long long nodes, unsigned long long tris) {
+            fprintf(stderr, "[trav] %s: rays %llu tree %llu (%.1f%%) chunks %llu rounds %llu lanes_with_ray/round %.2f | node steps %llu "
+                    "(%.2f/round) lanes/node step %.2f | tri steps %llu (%.2f/round) lanes/tri step %.2f | nodes/tree ray %.2f tris/tree ray %.2f\n",
+                    name, rays, tree, 100.0 * tree / (rays ? rays : 1), d[4], d[0], (double)d[1] / (d[0] ? d[0] : 1), d[2],
+                    (double)d[2] / (d[0] ? d[0] : 1), (double)nodes / (d[2] ? d[2] : 1), d[3], (double)d[3] / (d[0] ? d[0] : 1),
+                    (double)tris / (d[3] ? d[3] : 1), (double)nodes / (tree ? tree : 1), (double)tris / (tree ? tree : 1));
+        };
+        line("closest", hc.dbg, hc.cnt_closest, hc.cnt_tree_closest, hc.cnt_nodes_closest, hc.cnt_tris_closest);
+        line("shadow ", hc.dbg + 8, hc.cnt_shadow, hc.cnt_tree_shadow, nodes_shadow, tris_shadow);
+    }
     return 0;
 }
 

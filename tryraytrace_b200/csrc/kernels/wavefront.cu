@@ -21,27 +21,6 @@ constexpr int kCompactMinCap = 32 * 1024;  // the pool is not compacted below th
 
 TRT_DEV int pack_flags(int state, int depth, int mode) { return state | (depth << 8) | (mode << 16); }
 
-// Block-level queue append: every thread of the block calls this (converged); threads with
-// `want` get a distinct index in [old counter, old counter + n).  One global atomic per block.
-TRT_DEV int block_append(bool want, int* counter, int* smem_scratch /* >= 2 + warps ints */) {
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const unsigned m = __ballot_sync(0xffffffffu, want);
-    const int rank = __popc(m & ((1u << lane) - 1u));
-    if (lane == 0) smem_scratch[2 + warp] = __popc(m);
-    __syncthreads();
-    // every warp sums the counts of the warps before it (lane w reads warp w's count); warp 0 also
-    // has the block total and claims the range with the one atomic
-    const int n_warps = (int)(blockDim.x >> 5);
-    const int c = (int)lane < n_warps ? smem_scratch[2 + lane] : 0;
-    const int before = __reduce_add_sync(0xffffffffu, lane < warp ? c : 0);
-    if (warp == 0) {
-        const int total = __reduce_add_sync(0xffffffffu, c);
-        if (lane == 0) smem_scratch[0] = total ? atomicAdd(counter, total) : 0;
-    }
-    __syncthreads();
-    return smem_scratch[0] + before + rank;  // called once per kernel: the scratch is not reused
-}
-
 // ---- prepare: single thread, advances the queue bookkeeping between iterations --------
 __global__ void k_prepare(Control* ctl, int compact_quarters) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -72,7 +51,7 @@ __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->next_sample = 0;
     ctl->total_samples = total;
-    ctl->n_free = capacity;  // every slot is free (the free list is the identity)
+    ctl->n_free = 0;         // every slot is marked ended in the dead mask (k_init_pool); the first free scan lists them all
     ctl->active_cap = capacity;
     ctl->compact_go = 0;
     ctl->alive = capacity;   // prepare subtracts n_free and adds n_regen
@@ -85,6 +64,7 @@ __global__ void k_reset_counters(Control* ctl) {
     ctl->cnt_replays = ctl->cnt_iterations = 0;
     ctl->cnt_nodes_closest = ctl->cnt_tris_closest = 0;
     ctl->cnt_tree_closest = ctl->cnt_tree_shadow = 0;
+    for (int i = 0; i < 16; i++) ctl->dbg[i] = 0;
 }
 
 __global__ void k_reset_cursors(Control* ctl) {
@@ -160,12 +140,56 @@ __global__ void k_compact_commit(Control* ctl) {
     ctl->compact_go = 0;
 }
 
-__global__ void k_init_pool(PoolView pool, int* free_list) {
+__global__ void k_init_pool(PoolView pool) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool.capacity) return;
     pool.ray_d[i] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
     pool.sh_d[i] = make_float4(0.f, 0.f, 0.f, i2f(0));
-    if (free_list) free_list[i] = i;
+    if (pool.dead_mask && (i & 31) == 0) pool.dead_mask[i >> 5] = 0xffffffffu;
+}
+
+// ---- free scan: dead-mask words of the last shade pass -> free list ----------------------------
+// One thread per mask word (32 slots).  Block-level exclusive scan of the popcounts, one global atomic
+// per block on Control::n_free, then every thread writes the slots of its set bits.  The shade kernel
+// itself appends nothing (no block barrier, no atomic round trip on its critical path).
+constexpr int kScanBlock = 256;
+__global__ void __launch_bounds__(kScanBlock) k_free_scan(const uint32_t* __restrict__ dead_mask, int* __restrict__ free_list,
+                                                          Control* ctl) {
+    __shared__ int warp_sum[kScanBlock / 32];
+    __shared__ int block_base;
+    const int n_words = (ctl->active_cap + 31) >> 5;
+    const int w = blockIdx.x * kScanBlock + threadIdx.x;
+    if (blockIdx.x * kScanBlock >= n_words) return;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t m = w < n_words ? dead_mask[w] : 0u;
+    const int c = __popc(m);
+    int incl = c;  // inclusive scan within the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int ws = (int)lane < kScanBlock / 32 ? warp_sum[lane] : 0;
+        int wi = ws;
+#pragma unroll
+        for (int d = 1; d < kScanBlock / 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, d);
+            if ((int)lane >= d) wi += v;
+        }
+        if ((int)lane < kScanBlock / 32) warp_sum[lane] = wi - ws;  // exclusive prefix of the warp totals
+        if (lane == kScanBlock / 32 - 1) block_base = wi ? atomicAdd(&ctl->n_free, wi) : 0;
+    }
+    __syncthreads();
+    int at = block_base + warp_sum[warp] + incl - c;
+    const int first = w << 5;
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        free_list[at++] = first + b;
+    }
 }
 
 // ---- XORWOW column table: col_vecs[f*w + col] = M^col * v0(frame f) --------------------
@@ -271,9 +295,7 @@ __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev s
 // requested up front, before the state word has come back; in the drain phase of a job, when
 // most slots are dead, the loads wait for the state check instead.
 template <bool COUNT, bool FAST>
-__global__ void __launch_bounds__(kShadeMaxBlock) k_shade(PoolView pool, int* __restrict__ free_list, Control* ctl,
-                                                  SceneDev sc, JobParams job) {
-    __shared__ int scratch[2 + kShadeMaxBlock / 32];
+__global__ void __launch_bounds__(kShadeMaxBlock) k_shade(PoolView pool, Control* ctl, SceneDev sc, JobParams job) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of the block size
     const int cap = ctl->active_cap;                         // ... and so is the compacted bound
     if (slot == 0) ctl->cursor_shadow = 0;                   // the shadow kernel of this iteration starts at chunk 0
@@ -359,8 +381,9 @@ __global__ void __launch_bounds__(kShadeMaxBlock) k_shade(PoolView pool, int* __
             pool.sh_d[slot] = make_float4(0.f, 0.f, 0.f, i2f(0));
         }
     }
-    const int fi = block_append(terminated, &ctl->n_free, scratch);
-    if (terminated) free_list[fi] = slot;
+    // which slots ended: one mask word per warp (all 32 lanes are here); k_free_scan lists them
+    const unsigned ended = __ballot_sync(0xffffffffu, terminated);
+    if ((threadIdx.x & 31u) == 0) pool.dead_mask[slot >> 5] = ended;
 }
 
 // ---- shadow, reference order: any hit for every slot that holds a shadow ray ---------------
@@ -519,6 +542,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     st.cur = kWideEmptyRef;
     WideCounts wc = {0, 0};
     unsigned wc_tree = 0;
+    unsigned dbg_rounds = 0, dbg_has = 0, dbg_nsteps = 0, dbg_tsteps = 0, dbg_chunks = 0;
     bool has = false;
     int slot = -1;
     int qn = 0;  // warp-uniform: entries in the tree-ray queue
@@ -547,7 +571,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
                 q_s[qi] = my_slot;
             }
             qn += __popc(m);
-            if (COUNT && lane == 0) wc_tree += __popc(m);
+            if (COUNT && lane == 0) { wc_tree += __popc(m); dbg_chunks++; }
             fd.fresh = false;
             __syncwarp();
         }
@@ -570,9 +594,11 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             if (qn == 0 && feeder_exhausted(fd)) break;
             continue;
         }
+        if (COUNT && lane == 0) { dbg_rounds++; dbg_has += __popc(act); }
         // 3. node phase: up to `node_iters` node steps, while enough lanes still have node work
 #pragma unroll 1
         for (int it = 0; it < ph.node_iters; it++) {
+            if (COUNT && lane == 0) dbg_nsteps++;
             closest_node_step<E, S, COUNT, WIDE>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, closest_node_work(st, stk_base) && closest_has_room<E, S>(st));
             if (__popc(m) < ph.node_min) break;
@@ -580,6 +606,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         // 4. triangle phase: at least one step, more while enough lanes have a triangle waiting
 #pragma unroll 1
         for (;;) {
+            if (COUNT && lane == 0) dbg_tsteps++;
             closest_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, st.tp != stk_ttop);
             if (__popc(m) < ph.tri_min) break;
@@ -597,6 +624,11 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         warp_add(&ctl->cnt_nodes_closest, wc.nodes);
         warp_add(&ctl->cnt_tris_closest, wc.tris);
         warp_add(&ctl->cnt_tree_closest, wc_tree);
+        warp_add(&ctl->dbg[0], dbg_rounds);
+        warp_add(&ctl->dbg[1], dbg_has);
+        warp_add(&ctl->dbg[2], dbg_nsteps);
+        warp_add(&ctl->dbg[3], dbg_tsteps);
+        warp_add(&ctl->dbg[4], dbg_chunks);
     }
 }
 
@@ -642,6 +674,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     st.occluded = false;
     WideCounts wc = {0, 0};
     unsigned wc_tree = 0;
+    unsigned dbg_rounds = 0, dbg_has = 0, dbg_nsteps = 0, dbg_tsteps = 0, dbg_chunks = 0;
     bool has = false;
     int slot = -1;
     int qn = 0;
@@ -668,7 +701,7 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
                 q_d[qi] = make_float4(d4.x, d4.y, d4.z, i2f(my_slot));
             }
             qn += __popc(m);
-            if (COUNT && lane == 0) wc_tree += __popc(m);
+            if (COUNT && lane == 0) { wc_tree += __popc(m); dbg_chunks++; }
             fd.fresh = false;
             __syncwarp();
         }
@@ -690,14 +723,17 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             if (qn == 0 && feeder_exhausted(fd)) break;
             continue;
         }
+        if (COUNT && lane == 0) { dbg_rounds++; dbg_has += __popc(act); }
 #pragma unroll 1
         for (int it = 0; it < ph.node_iters; it++) {
+            if (COUNT && lane == 0) dbg_nsteps++;
             shadow_node_step<E, S, COUNT, WIDE>(s_nodes, k_smem, sc, st, stk_base, spill, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, shadow_node_work(st, stk_base) && shadow_has_room<E, S>(st));
             if (__popc(m) < ph.node_min) break;
         }
 #pragma unroll 1
         for (;;) {
+            if (COUNT && lane == 0) dbg_tsteps++;
             shadow_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, !st.occluded && st.tp != stk_ttop);
             if (__popc(m) < ph.tri_min) break;
@@ -717,6 +753,11 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         warp_add(&ctl->cnt_nodes, wc.nodes);
         warp_add(&ctl->cnt_tris, wc.tris);
         warp_add(&ctl->cnt_tree_shadow, wc_tree);
+        warp_add(&ctl->dbg[8], dbg_rounds);
+        warp_add(&ctl->dbg[9], dbg_has);
+        warp_add(&ctl->dbg[10], dbg_nsteps);
+        warp_add(&ctl->dbg[11], dbg_tsteps);
+        warp_add(&ctl->dbg[12], dbg_chunks);
     }
 }
 
@@ -953,7 +994,8 @@ int wf_fast_max_smem_nodes(int threads, size_t smem_limit) {
 
 void wf_init_pool(const PoolView& pool, int* free_list, Control* ctl, cudaStream_t s) {
     (void)ctl;
-    k_init_pool<<<grid_for(pool.capacity), kBlock, 0, s>>>(pool, free_list);
+    (void)free_list;
+    k_init_pool<<<grid_for(pool.capacity), kBlock, 0, s>>>(pool);
 }
 
 void wf_reset_counters(Control* ctl, cudaStream_t s) { k_reset_counters<<<1, 32, 0, s>>>(ctl); }
@@ -993,8 +1035,11 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
     auto mark = [&](int i, cudaStream_t on) { if (marks && ((st.mark_mask >> i) & 1)) cudaEventRecord(marks[i], on); };
     if (overlap) cudaStreamWaitEvent(side, st.fork, 0);
     mark(0, side);
+    const int visit = min(pool.capacity, st.visit_cap);
+    // slots that ended in the last shade pass -> free list + count (the count also feeds `alive` in the drain phase)
+    k_free_scan<<<((visit + 31) / 32 + kScanBlock - 1) / kScanBlock, kScanBlock, 0, side>>>(pool.dead_mask, free_list, ctl);
     k_prepare<<<1, 32, 0, side>>>(ctl, dims.compact_quarters);
-    launched++;
+    launched += 2;
     if (st.samples_left) {
         // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
         // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up;
@@ -1010,7 +1055,6 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
         cudaEventRecord(st.join, side);
         cudaStreamWaitEvent(s, st.join, 0);
     }
-    const int visit = min(pool.capacity, st.visit_cap);
     if (compact_lists && visit > kCompactMinCap) {  // the host launches these only once the job is close to its drain phase
         int* list_a = compact_lists;
         int* list_b = compact_lists + pool.capacity / 2 + 512;
@@ -1025,7 +1069,7 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
     mark(3, s);
     // blocks beyond active_cap return at once, but 16 Ki of them still cost 0.1 ms: size the grid by the bound
     const int shade_blocks = (visit + dims.shade_block - 1) / dims.shade_block;
-    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<shade_blocks, dims.shade_block, 0, s>>>(pool, free_list, ctl, sc, job);
+    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<shade_blocks, dims.shade_block, 0, s>>>(pool, ctl, sc, job);
     mark(4, s);
     if (st.overlap) cudaEventRecord(st.fork, s);  // the next side part may start now
     if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);

@@ -33,6 +33,8 @@ struct PoolView {
     float4* sh_d;    // shadow ray of this slot: direction.xyz, valid flag (int bits, 1 = trace it)
     uint4* rng_a;    // XORWOW v0..v3
     uint2* rng_b;    // XORWOW v4, d
+    uint32_t* dead_mask;  // render pool only: bit b of word w = slot 32*w+b ended in the last shade pass (k_free_scan
+                          // turns the words into the free list the next regenerate consumes)
     int capacity;    // multiple of 256 (512 for the render pool: the shade CTA size)
 };
 
@@ -53,6 +55,10 @@ struct Control {
     unsigned long long cnt_nodes, cnt_tris;                // all queries (COUNT builds only)
     unsigned long long cnt_nodes_closest, cnt_tris_closest;  // closest-hit queries only
     unsigned long long cnt_tree_closest, cnt_tree_shadow;    // queries that entered the tree (COUNT builds only)
+    // lane-utilisation statistics of the persistent traversal kernels (COUNT builds only; printed by
+    // trt_get_counters when TRT_TRAV_STATS is set): [0..4] closest, [8..12] shadow:
+    // rounds, sum of lanes holding a ray per round, warp-level node steps, warp-level triangle steps, top-phase chunks
+    unsigned long long dbg[16];
 };
 
 // Per-job constants handed to the kernels by value.
