@@ -296,7 +296,9 @@ LaunchDims launch_dims(const trt_ctx* c) {
     if (const char* e = getenv("TRT_WIDE_LOADS")) d.wide_loads = atoi(e) != 0;
     d.refill_below = 32;
     d.regen_block = 128;
-    d.shade_block = 512;
+    d.shade_block = 128;
+    d.shade_minb = 8;
+    if (const char* e = getenv("TRT_SHADE_MINB")) d.shade_minb = atoi(e);
     if (const char* e = getenv("TRT_SHADE_BLOCK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512) d.shade_block = v; }
     if (const char* e = getenv("TRT_REGEN_BLOCK")) d.regen_block = std::max(32, std::min(256, atoi(e) / 32 * 32));
     d.compact_quarters = 3;
@@ -417,6 +419,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         if (st.overlap) CU(cudaEventRecord(st.fork, c->stream));
         st.visit_cap = c->pool_cap;
         st.samples_left = true;
+        st.mostly_live = true;
         // Issue batches of iterations, staying one batch ahead of the completion poll.
         // near_drain: the job can reach its drain phase within the batches in flight (the poll is up to two
         // batches old; an iteration starts about capacity / 6 samples) -- from here on the batches are short.
@@ -466,6 +469,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
             // the bound is fresh and few iterations are queued behind the last live path
             st.visit_cap = std::min(st.visit_cap, hc.active_cap);
             if (hc.next_sample == hc.total_samples) st.samples_left = false;
+            st.mostly_live = (long long)hc.alive * 2 > (long long)hc.active_cap;
             if (near_drain) batch = kTailBatchIterations;
             b++;
             if (issued > max_iterations) {

@@ -83,7 +83,14 @@ TRT_DEV bool shade_vertex(const SceneDev& sc, const RenderConsts& rc, PathVertex
         u *= 0.01f;
         v *= 0.01f;
         v = 1.0f - v;
-        const float4 tx = tex2D<float4>(sc.tex[tex_id], u, v);
+        // (a chain of selects instead of sc.tex[tex_id]: a dynamic index would force the whole parameter
+        // struct into local memory)
+        cudaTextureObject_t to = sc.tex[0];
+        if (tex_id == 1) to = sc.tex[1];
+        if (tex_id == 2) to = sc.tex[2];
+        if (tex_id == 3) to = sc.tex[3];
+        if (tex_id == 4) to = sc.tex[4];
+        const float4 tx = tex2D<float4>(to, u, v);
         albedo = v_mul(albedo, f3(tx.x, tx.y, tx.z));
     }
 
@@ -107,11 +114,18 @@ TRT_DEV bool shade_vertex(const SceneDev& sc, const RenderConsts& rc, PathVertex
     const float p_spec = w_spec / sum;
     const float p_trans = w_trans / sum;
 
-    if (io.depth > rc.rr_threshold) {  // Russian roulette (:559-565)
+    {  // Russian roulette (:559-565).  Written without a branch around the draw: an early return inside a
+       // conditional makes the function exit the reconvergence point, and the lanes that played and the lanes
+       // that did not would run the whole rest of the vertex one group after the other.
+        const bool play = io.depth > rc.rr_threshold;
         float p = albedo_max;
         if (p < 0.05f) p = 0.05f;
-        if (xw_uniform(io.rng) < p) io.thr = v_scale(io.thr, 1.0f / p);
-        else return false;
+        Xorwow drawn = io.rng;
+        const float u = xw_uniform(drawn);
+        if (play) io.rng = drawn;
+        if (play && !(u < p)) return false;
+        const float boost = play ? 1.0f / p : 1.0f;
+        if (play) io.thr = v_scale(io.thr, boost);
     }
 
     const float rnd = xw_uniform(io.rng);

@@ -294,13 +294,14 @@ __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev s
 // loads are in flight, so while the pool is mostly live (`eager`) every array of the slot is
 // requested up front, before the state word has come back; in the drain phase of a job, when
 // most slots are dead, the loads wait for the state check instead.
-template <bool COUNT, bool FAST>
-__global__ void __launch_bounds__(kShadeMaxBlock) k_shade(PoolView pool, Control* ctl, SceneDev sc, JobParams job) {
+template <bool COUNT, bool FAST, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_shade(PoolView pool, Control* ctl, SceneDev sc, JobParams job, int eager) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of the block size
-    const int cap = ctl->active_cap;                         // ... and so is the compacted bound
     if (slot == 0) ctl->cursor_shadow = 0;                   // the shadow kernel of this iteration starts at chunk 0
-    if (blockIdx.x * blockDim.x >= cap) return;              // whole block beyond the visited prefix
-    const bool eager = ctl->alive * 2 > cap;
+    // The state loads go out BEFORE anything that depends on the control block has come back (the grid is
+    // sized by the host's bound, every slot below it is valid memory): a dependent read of the control block
+    // first cost every CTA an L2 round trip before its first state load.  `eager` is the host's knowledge
+    // (samples are still being handed out, the pool is mostly live).
     const float4 d4 = pool.ray_d[slot];
     float4 thr4, rad4, pend4, o4;
     float2 hit;
@@ -310,6 +311,8 @@ __global__ void __launch_bounds__(kShadeMaxBlock) k_shade(PoolView pool, Control
         thr4 = pool.thr[slot]; rad4 = pool.rad[slot]; pend4 = pool.pend[slot]; o4 = pool.ray_o[slot];
         hit = pool.hit[slot]; ra = pool.rng_a[slot]; rb = pool.rng_b[slot];
     }
+    const int cap = ctl->active_cap;                         // a multiple of the block size
+    if (blockIdx.x * blockDim.x >= cap) return;              // whole block beyond the visited prefix
     const int flags = f2i(d4.w);
     const int state = flags & 0xff;
     bool terminated = false;
@@ -1069,7 +1072,18 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
     mark(3, s);
     // blocks beyond active_cap return at once, but 16 Ki of them still cost 0.1 ms: size the grid by the bound
     const int shade_blocks = (visit + dims.shade_block - 1) / dims.shade_block;
-    k_shade<COUNT, MODE == TRT_TRAVERSE_FAST><<<shade_blocks, dims.shade_block, 0, s>>>(pool, ctl, sc, job);
+    constexpr bool F = MODE == TRT_TRAVERSE_FAST;
+    const int eager = (st.samples_left || st.mostly_live) ? 1 : 0;
+    if (dims.shade_block == 128) {
+        switch (dims.shade_minb) {
+        case 10: k_shade<COUNT, F, 128, 10><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
+        case 12: k_shade<COUNT, F, 128, 12><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
+        case 14: k_shade<COUNT, F, 128, 14><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
+        default: k_shade<COUNT, F, 128, 8><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
+        }
+    } else {
+        k_shade<COUNT, F, kShadeMaxBlock, 2><<<shade_blocks, dims.shade_block, 0, s>>>(pool, ctl, sc, job, eager);
+    }
     mark(4, s);
     if (st.overlap) cudaEventRecord(st.fork, s);  // the next side part may start now
     if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);

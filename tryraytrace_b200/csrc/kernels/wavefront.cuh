@@ -90,6 +90,7 @@ struct LaunchDims {
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
     int shade_block;    // threads per shade CTA (64 .. 512; the pool capacity is a multiple of 512): larger CTAs, fewer
                         // free-list atomics and barriers waiting on them
+    int shade_minb;     // 128-thread shade CTAs: resident CTAs per SM the register allocation aims for (8, 10, 12, 14)
     int regen_block;    // threads per regenerate CTA (it shares SMs with the persistent shadow CTAs)
     int compact_quarters;  // drain phase: compact when live paths <= this many quarters of the visited slots (1..3)
     Phases closest_phases, shadow_phases;
@@ -119,6 +120,7 @@ struct IterStreams {
     // and next_sample only grows within a job)
     int visit_cap = 0x7fffffff;  // upper bound of Control::active_cap: sizes the shade grid
     bool samples_left = true;    // false: the job has handed out its last sample, nothing to regenerate
+    bool mostly_live = true;     // at least half of the visited slots hold a path: shade requests a slot's whole state up front
 };
 // one wavefront iteration on the streams of `st`; returns the number of kernels it launched
 // `marks`, when not null, receives six events: [0] prepare+regenerate [1]  and  [2] extend [3] shade [4] shadow [5]
