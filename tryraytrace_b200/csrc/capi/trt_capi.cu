@@ -304,13 +304,16 @@ LaunchDims launch_dims(const trt_ctx* c) {
     d.compact_quarters = 3;
     if (const char* e = getenv("TRT_COMPACT_QUARTERS")) d.compact_quarters = std::max(1, std::min(3, atoi(e)));
     if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
-    d.closest_phases = Phases{2, 12, 8};
-    d.shadow_phases = Phases{2, 12, 8};
+    int ranked = 0;  // measured equal to the brute-force pass on C2 (65.4 vs 65.7 ms of extend per 64 spp): kept as an option
+    if (const char* e = getenv("TRT_RANKED_TOP")) ranked = atoi(e) != 0;
+    d.closest_phases = Phases{2, 12, 8, ranked};
+    d.shadow_phases = Phases{2, 12, 8, 0};
     if (const char* e = getenv("TRT_PHASES")) {  // "iters,node_min,tri_min[,iters,node_min,tri_min]" closest[,shadow]
         int v[6] = {1, 33, 33, 1, 33, 33};
         const int n = sscanf(e, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
-        if (n >= 3) d.closest_phases = d.shadow_phases = Phases{std::max(1, v[0]), v[1], std::max(1, v[2])};
-        if (n >= 6) d.shadow_phases = Phases{std::max(1, v[3]), v[4], std::max(1, v[5])};
+        if (n >= 3) d.closest_phases = d.shadow_phases = Phases{std::max(1, v[0]), v[1], std::max(1, v[2]), 0};
+        if (n >= 6) d.shadow_phases = Phases{std::max(1, v[3]), v[4], std::max(1, v[5]), 0};
+        d.closest_phases.ranked_top = ranked;
     }
     return d;
 }
@@ -335,23 +338,69 @@ void fill_job(trt_ctx* c, JobParams& job, float* d_accum, int w, int h, int firs
 // Sorts the root-level list by the axis on which each leaf box is thinnest and fills the per-axis
 // counts and planes the shadow top phase reads (kernels/common.cuh TopPrims).
 void finalize_top(TopPrims& tp) {
-    struct Item { float4 v0, e1, e2, bmin, bmax; int axis; };
+    struct Item { float4 v0, e1, e2, bmin, bmax; int axis; int small; };
     std::vector<Item> items(tp.n);
+    // small primitives (lights): box area below 2 % of the box around the whole list and the tree; at most 4
+    float lo[3] = {tp.root_lo.x, tp.root_lo.y, tp.root_lo.z}, hi[3] = {tp.root_hi.x, tp.root_hi.y, tp.root_hi.z};
+    auto area = [](const float* a, const float* b) {
+        const float x = std::max(b[0] - a[0], 0.f), y = std::max(b[1] - a[1], 0.f), z = std::max(b[2] - a[2], 0.f);
+        return 2.f * (x * y + y * z + z * x);
+    };
+    for (int i = 0; i < tp.n; i++) {
+        const float bl[3] = {tp.bmin[i].x, tp.bmin[i].y, tp.bmin[i].z}, bh[3] = {tp.bmax[i].x, tp.bmax[i].y, tp.bmax[i].z};
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], bl[k]); hi[k] = std::max(hi[k], bh[k]); }
+    }
+    const float scene_area = area(lo, hi);
+    int n_small = 0;
     for (int i = 0; i < tp.n; i++) {
         const float ext[3] = {tp.bmax[i].x - tp.bmin[i].x, tp.bmax[i].y - tp.bmin[i].y, tp.bmax[i].z - tp.bmin[i].z};
         int ax = 0;
         for (int k = 1; k < 3; k++)
             if (ext[k] < ext[ax]) ax = k;
-        items[i] = Item{tp.v0[i], tp.e1[i], tp.e2[i], tp.bmin[i], tp.bmax[i], ax};
+        const float bl[3] = {tp.bmin[i].x, tp.bmin[i].y, tp.bmin[i].z}, bh[3] = {tp.bmax[i].x, tp.bmax[i].y, tp.bmax[i].z};
+        const int small = (area(bl, bh) < 0.02f * scene_area && n_small < 4) ? 1 : 0;
+        n_small += small;
+        items[i] = Item{tp.v0[i], tp.e1[i], tp.e2[i], tp.bmin[i], tp.bmax[i], ax, small};
     }
-    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.axis < b.axis; });
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+        return a.axis != b.axis ? a.axis < b.axis : a.small < b.small;
+    });
     tp.n_axis[0] = tp.n_axis[1] = tp.n_axis[2] = 0;
+    tp.n_thin[0] = tp.n_thin[1] = tp.n_thin[2] = 0;
+    tp.n_full = 0;
     for (int i = 0; i < tp.n; i++) {
         const Item& it = items[i];
         tp.v0[i] = it.v0; tp.e1[i] = it.e1; tp.e2[i] = it.e2; tp.bmin[i] = it.bmin; tp.bmax[i] = it.bmax;
         tp.thin_lo[i] = it.axis == 0 ? it.bmin.x : (it.axis == 1 ? it.bmin.y : it.bmin.z);
         tp.thin_hi[i] = it.axis == 0 ? it.bmax.x : (it.axis == 1 ? it.bmax.y : it.bmax.z);
+        tp.thin2[i] = make_float2(tp.thin_lo[i], tp.thin_hi[i]);
         tp.n_axis[it.axis]++;
+        if (it.small) tp.full_idx[tp.n_full++] = i;
+        else tp.n_thin[it.axis]++;
+    }
+    // pairs in ascending object index (kernels/common.cuh TopPrims::pair_*)
+    std::vector<int> order(tp.n);
+    for (int i = 0; i < tp.n; i++) order[i] = i;
+    auto obj_id = [&](int i) { int v; memcpy(&v, &tp.v0[i].w, 4); return v & 0x3fffffff; };
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return obj_id(a) < obj_id(b); });
+    tp.n_pairs = (tp.n + 1) / 2;
+    for (int j = 0; j < tp.n_pairs; j++) {
+        float v[2][3] = {{0, 0, 0}, {0, 0, 0}}, a[2][3] = {{0, 0, 0}, {0, 0, 0}}, b[2][3] = {{0, 0, 0}, {0, 0, 0}};
+        int id[2] = {-1, -1};
+        for (int k = 0; k < 2 && 2 * j + k < tp.n; k++) {
+            const int i = order[2 * j + k];
+            v[k][0] = tp.v0[i].x; v[k][1] = tp.v0[i].y; v[k][2] = tp.v0[i].z;
+            a[k][0] = tp.e1[i].x; a[k][1] = tp.e1[i].y; a[k][2] = tp.e1[i].z;
+            b[k][0] = tp.e2[i].x; b[k][1] = tp.e2[i].y; b[k][2] = tp.e2[i].z;
+            memcpy(&id[k], &tp.v0[i].w, 4);
+        }
+        for (int c = 0; c < 3; c++) {
+            tp.pair_nv0[j][c] = make_float2(-v[0][c], -v[1][c]);
+            tp.pair_e1[j][c] = make_float2(a[0][c], a[1][c]);
+            tp.pair_ne1[j][c] = make_float2(-a[0][c], -a[1][c]);
+            tp.pair_e2[j][c] = make_float2(b[0][c], b[1][c]);
+        }
+        tp.pair_id[j] = make_int2(id[0], id[1]);
     }
 }
 

@@ -94,6 +94,24 @@ struct TopPrims {
     float thin_lo[kMaxTop], thin_hi[kMaxTop];
     int n_axis[3];
     int n;
+    // Closest-hit ranking (traverse_fast.cuh top_rank): inside each axis group the oversized primitives (walls)
+    // come first -- n_thin[a] of them, ranked by the thin axis alone; (thin_lo, thin_hi) again as one 8-byte
+    // record -- and the small ones (light sources) last; those are listed in full_idx and ranked by the slab
+    // interval of their whole leaf box.
+    float2 thin2[kMaxTop];
+    int n_thin[3];
+    int n_full;
+    int full_idx[4];
+    // Closest-hit brute-force pass, two primitives per instruction (traverse_fast.cuh tri_test_pair): pair j holds
+    // the primitives of rank 2j and 2j+1 in ASCENDING OBJECT INDEX (so a tie in t never replaces the earlier one and
+    // the update is a plain `<`), component-interleaved: .x = first, .y = second primitive of the pair.  An odd
+    // count is padded with a degenerate triangle (zero edges: rejected by the determinant test).
+    float2 pair_nv0[kMaxTop / 2][3];  // -v0   (o + (-v0) == o - v0 bit for bit)
+    float2 pair_e1[kMaxTop / 2][3];
+    float2 pair_ne1[kMaxTop / 2][3];  // -e1   (the reference negates the rounded product; (-a)*b == -(a*b))
+    float2 pair_e2[kMaxTop / 2][3];
+    int2 pair_id[kMaxTop / 2];        // object id | kTriNoDerive
+    int n_pairs;
 };
 
 struct RenderConsts {

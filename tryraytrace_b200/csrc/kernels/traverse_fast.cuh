@@ -184,6 +184,47 @@ TRT_DEV float2 mul2(float2 a, float s) {
         : "f"(a.x), "f"(a.y), "f"(s));
     return r;
 }
+// pair x pair / pair x scalar forms used by the two-triangle test (tri_test_pair)
+TRT_DEV float2 mul2p(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.ftz.f32x2 rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+TRT_DEV float2 add2(float2 a, float s) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+        "add.rn.ftz.f32x2 rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(s));
+    return r;
+}
+TRT_DEV float2 sub2p(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "sub.rn.ftz.f32x2 rr, ra, rb;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+TRT_DEV float2 fma2p(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.ftz.f32x2 rr, ra, rb, rc;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+TRT_DEV float2 fma2s(float2 a, float s, float2 c) {
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rc, rr;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+        "fma.rn.ftz.f32x2 rr, ra, rb, rc;\n\tmov.b64 {%0, %1}, rr;\n\t}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a.x), "f"(a.y), "f"(s), "f"(c.x), "f"(c.y));
+    return r;
+}
 // (plane - o) * inv for the four children of one plane vector
 TRT_DEV float4 plane_t(float4 p, float o, float inv) {
     const float2 a = mul2(sub2(make_float2(p.x, p.y), o), inv);
@@ -241,6 +282,35 @@ TRT_DEV float tri_test_flat(const F3 v0, const F3 e1, const F3 e2, const F3 o, c
     const float t = p_mul(f, x_dot(e2, q));
     const bool ok = !(a > -eps && a < eps) && !(u < 0.f || u > 1.f) && !(v < 0.f || p_add(u, v) > 1.f) && t > eps;
     return ok ? t : 0.f;
+}
+
+// The same test for TWO triangles at once (sm_100 packed FP32: FFMA2 / FMUL2 / FADD2).  Every packed lane is
+// rounded exactly like the scalar instruction, and each line below is the packed form of the corresponding line
+// of tri_test_flat with the same operand roles: multiplication commutes, o + (-v0) == o - v0, and the negated
+// rounded product -(x * y) of the reference's cross product is the product with one operand negated.
+// nv0 = -v0, ne1 = -e1, nd = -d.  Returns t per triangle, 0 = no hit.
+TRT_DEV float2 tri_test_pair(const float2 nv0[3], const float2 e1[3], const float2 ne1[3], const float2 e2[3], const F3 o,
+                             const F3 d, const F3 nd) {
+    const float eps = 1e-5f;
+    // h = cross(d, e2)
+    const float2 hx = fma2s(e2[2], d.y, mul2(e2[1], nd.z));
+    const float2 hy = fma2s(e2[0], d.z, mul2(e2[2], nd.x));
+    const float2 hz = fma2s(e2[1], d.x, mul2(e2[0], nd.y));
+    // a = dot(e1, h)
+    const float2 a = fma2p(e1[2], hz, fma2p(e1[0], hx, mul2p(e1[1], hy)));
+    const float2 f = make_float2(p_rcp(a.x), p_rcp(a.y));
+    // s = o - v0
+    const float2 sx = add2(nv0[0], o.x), sy = add2(nv0[1], o.y), sz = add2(nv0[2], o.z);
+    const float2 u = mul2p(f, fma2p(sz, hz, fma2p(sx, hx, mul2p(sy, hy))));
+    // q = cross(s, e1)
+    const float2 qx = fma2p(sy, e1[2], mul2p(sz, ne1[1]));
+    const float2 qy = fma2p(sz, e1[0], mul2p(sx, ne1[2]));
+    const float2 qz = fma2p(sx, e1[1], mul2p(sy, ne1[0]));
+    const float2 v = mul2p(f, fma2s(qz, d.z, fma2s(qx, d.x, mul2(qy, d.y))));
+    const float2 t = mul2p(f, fma2p(e2[2], qz, fma2p(e2[0], qx, mul2p(e2[1], qy))));
+    const bool ok0 = !(a.x > -eps && a.x < eps) && !(u.x < 0.f || u.x > 1.f) && !(v.x < 0.f || p_add(u.x, v.x) > 1.f) && t.x > eps;
+    const bool ok1 = !(a.y > -eps && a.y < eps) && !(u.y < 0.f || u.y > 1.f) && !(v.y < 0.f || p_add(u.y, v.y) > 1.f) && t.y > eps;
+    return make_float2(ok0 ? t.x : 0.f, ok1 ? t.y : 0.f);
 }
 
 // Slab interval of one child from its near/far planes (selected by the sign of the inverse
@@ -360,14 +430,121 @@ TRT_DEV TopResult top_closest(const TopPrims& top, const F3 o, const F3 d) {
     TopResult r;
     r.d_min = 1e20f;
     r.id = -1;
+    const F3 nd = f3(-d.x, -d.y, -d.z);
+    // two primitives per pass, in ascending object index: on a tie in t the earlier (lower) index stays
 #pragma unroll 1
-    for (int p = 0; p < top.n; p++) {
-        const float4 a = top.v0[p], b = top.e1[p], c = top.e2[p];
-        const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
-        const int tid = f2i(a.w);
-        if (t > 0.f && (t < r.d_min || (t == r.d_min && (tid & kTriIdMask) < (r.id & kTriIdMask)))) {
-            r.d_min = t;
-            r.id = tid;
+    for (int j = 0; j < top.n_pairs; j++) {
+        const float2 t = tri_test_pair(top.pair_nv0[j], top.pair_e1[j], top.pair_ne1[j], top.pair_e2[j], o, d, nd);
+        const int2 tid = top.pair_id[j];
+        if (t.x > 0.f && t.x < r.d_min) { r.d_min = t.x; r.id = tid.x; }
+        if (t.y > 0.f && t.y < r.d_min) { r.d_min = t.y; r.id = tid.y; }
+    }
+    float tn;
+    const float limit = r.d_min * kCullSlack;
+    r.enters = child_interval(sx ? top.root_hi.x : top.root_lo.x, sx ? top.root_lo.x : top.root_hi.x,
+                              sy ? top.root_hi.y : top.root_lo.y, sy ? top.root_lo.y : top.root_hi.y,
+                              sz ? top.root_hi.z : top.root_lo.z, sz ? top.root_lo.z : top.root_hi.z, o, inv, 0.f,
+                              limit, &tn);
+    return r;
+}
+
+// TOP PHASE, closest hit, RANKED.  The brute-force pass above runs the full triangle test for every
+// root-level primitive (seven per ray in the benchmark scenes) although a ray inside the room can only hit
+// the one or two walls in front of it.  Here every lane first ranks the primitives by where its ray enters
+// their reference leaf box -- on the box's thinnest axis only (two products, exactly the reference's; flat
+// wall boxes are 2e-3 thick, so this is the plane distance), or on all three axes for primitives flagged small
+// (lights) -- and then tests them nearest first until no untested primitive's entry lies below d_min * slack.
+// Skipping is exact for the same reasons as in the tree phase:
+//   * exit <= 0 (or an empty interval): the reference's slab test of that leaf box fails (its tmax is at most
+//     this axis' exit; no NaN can arise because safe_inv keeps the reciprocals finite), so the reference
+//     never tests the triangle either;
+//   * entry >= d_min * slack: the triangle lies inside its leaf box, its hit distance is not below the box
+//     entry (up to rounding far smaller than the slack), so it cannot beat the winner.  The winner itself is
+//     verified where it is consumed (resolve_hit), as always.
+// The per-lane triangle operands come from a shared-memory copy of the list (s_top: v0|id, e1, e2 per
+// primitive); lanes usually test one primitive (the wall their ray hits), the warp leaves the loop when no
+// lane has a candidate left.
+// Ranking pass: the three nearest candidates (keys k1 <= k2 <= k3, 0xffffffff = none).  FIRST: all primitives;
+// otherwise only those not in `tested` whose box entry lies below `limit`.
+template <bool FIRST>
+TRT_DEV void top_rank(const TopPrims& top, const F3 o, const F3 inv, unsigned tested, float limit, unsigned& k1,
+                      unsigned& k2, unsigned& k3) {
+    k1 = k2 = k3 = 0xffffffffu;
+    auto insert = [&](int p, float tn, bool ok) {
+        // key: entry distance (>= 0, so the bit pattern orders like the value) with the index in the low bits
+        if (!FIRST) ok = ok && tn < limit && !((tested >> p) & 1u);
+        const unsigned k = ok ? ((__float_as_uint(fmaxf(tn, 0.f)) & ~15u) | (unsigned)p) : 0xffffffffu;
+        const unsigned a = max(k1, k);
+        k1 = min(k1, k);
+        const unsigned b = max(k2, a);
+        k2 = min(k2, a);
+        k3 = min(k3, b);
+    };
+    auto thin = [&](int p, float oa, float ia) {
+        const float2 t = mul2(sub2(top.thin2[p], oa), ia);  // the reference's two products on this axis
+        insert(p, fminf(t.x, t.y), fmaxf(t.x, t.y) > 0.f);
+    };
+    int p = 0;
+#pragma unroll 1
+    for (const int e = top.n_thin[0]; p < e; p++) thin(p, o.x, inv.x);
+    p = top.n_axis[0];
+#pragma unroll 1
+    for (const int e = p + top.n_thin[1]; p < e; p++) thin(p, o.y, inv.y);
+    p = top.n_axis[0] + top.n_axis[1];
+#pragma unroll 1
+    for (const int e = p + top.n_thin[2]; p < e; p++) thin(p, o.z, inv.z);
+#pragma unroll 1
+    for (int i = 0; i < top.n_full; i++) {  // small primitives: the whole leaf box
+        const int q = top.full_idx[i];
+        const float4 lo = top.bmin[q], hi = top.bmax[q];
+        const float2 x = mul2(sub2(make_float2(lo.x, hi.x), o.x), inv.x);
+        const float2 y = mul2(sub2(make_float2(lo.y, hi.y), o.y), inv.y);
+        const float2 z = mul2(sub2(make_float2(lo.z, hi.z), o.z), inv.z);
+        const float tn = fmaxf(fmaxf(fminf(x.x, x.y), fminf(y.x, y.y)), fminf(z.x, z.y));
+        const float tf = fminf(fminf(fmaxf(x.x, x.y), fmaxf(y.x, y.y)), fmaxf(z.x, z.y));
+        insert(q, tn, tf > 0.f && tf >= tn);
+    }
+}
+
+TRT_DEV TopResult top_closest_ranked(const TopPrims& top, const float4* s_top, const F3 o, const F3 d, bool live) {
+    const F3 inv = f3(ref_safe_inv(d.x), ref_safe_inv(d.y), ref_safe_inv(d.z));
+    const bool sx = inv.x < 0.f, sy = inv.y < 0.f, sz = inv.z < 0.f;
+    TopResult r;
+    r.d_min = 1e20f;
+    r.id = -1;
+    unsigned k1, k2, k3, tested = 0;
+    top_rank<true>(top, o, inv, 0u, 0.f, k1, k2, k3);
+    if (!live) k1 = 0xffffffffu;
+    bool had3 = k3 != 0xffffffffu;  // there may be candidates beyond the three ranked ones
+#pragma unroll 1
+    for (;;) {
+        // the nearest untested candidate, if it can still beat (or tie) the winner; the candidates are sorted,
+        // so when it cannot, nothing behind it can
+        const bool go = k1 != 0xffffffffu && __uint_as_float(k1 & ~15u) < r.d_min * kCullSlack;
+        if (!__any_sync(0xffffffffu, go)) break;
+        bool again = false;
+        if (go) {
+            const int p = (int)(k1 & 15u);
+            const float4 a = s_top[p * 3], b = s_top[p * 3 + 1], c = s_top[p * 3 + 2];
+            const float t = tri_test_flat(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), o, d);
+            const int tid = f2i(a.w);
+            if (t > 0.f && (t < r.d_min || (t == r.d_min && (tid & kTriIdMask) < (r.id & kTriIdMask)))) {
+                r.d_min = t;
+                r.id = tid;
+            }
+            tested |= 1u << p;
+            k1 = k2;
+            k2 = k3;
+            k3 = 0xffffffffu;
+            again = k1 == 0xffffffffu && had3;  // used up the ranked three and there may be more: rank the rest (rare)
+        } else {
+            k1 = 0xffffffffu;
+            had3 = false;
+        }
+        if (__any_sync(0xffffffffu, again)) {
+            unsigned n1, n2, n3;
+            top_rank<false>(top, o, inv, tested, r.d_min * kCullSlack, n1, n2, n3);
+            if (again) { k1 = n1; k2 = n2; k3 = n3; had3 = n3 != 0xffffffffu; }
         }
     }
     float tn;

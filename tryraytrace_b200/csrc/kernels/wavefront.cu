@@ -433,6 +433,7 @@ constexpr int kStageBytesPerWarp = 2 * 2 * kChunk * 16;  // 2 buffers x (o + d) 
 constexpr int kQueueCap = 48;                             // entries; the top phase runs while <= kQueueLow are queued
 constexpr int kQueueLow = kQueueCap - kChunk;
 constexpr int kQueueBytesClosest = kQueueCap * (16 + 16 + 4);
+constexpr int kTopStageBytes = 3 * kMaxTop * 16;          // closest-hit kernel: shared-memory copy of the root-level list
 constexpr int kQueueBytesShadow = kQueueCap * (16 + 16);
 
 template <int THREADS> struct FastCfg;
@@ -440,8 +441,11 @@ template <> struct FastCfg<512>  { static constexpr int SC = 16, SS = 16; };
 template <> struct FastCfg<768>  { static constexpr int SC = 12, SS = 12; };
 template <> struct FastCfg<1024> { static constexpr int SC = 8,  SS = 10; };
 
+constexpr int kClaimChunks = 4;  // chunks a warp claims per atomic on the global cursor (one round trip per 128 slots)
+
 struct Feeder {  // warp-uniform state of the staging double buffer
     int cur_buf, cur_base, nxt_base;
+    int claim_base, claim_end;  // slots of the current claim not yet requested: [claim_base, claim_end)
     bool fresh;    // the current buffer holds a chunk that has not been processed yet
     bool nxt_req;  // a bulk copy into the other buffer has been issued
     bool drained;  // the global cursor ran past the pool
@@ -452,6 +456,7 @@ TRT_DEV void feeder_init(Feeder& f) {
     f.cur_buf = 0;
     f.cur_base = 0;
     f.nxt_base = 0;
+    f.claim_base = f.claim_end = 0;
     f.fresh = false;
     f.nxt_req = false;
     f.drained = false;
@@ -483,9 +488,15 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
         }
     }
     if (!f.nxt_req && !f.drained) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, kChunk);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        if (f.claim_base >= f.claim_end) {  // claim the next kClaimChunks chunks
+            int c = 0;
+            if (lane == 0) c = atomicAdd(cursor, kClaimChunks * kChunk);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            f.claim_base = c;
+            f.claim_end = min(c + kClaimChunks * kChunk, limit);  // limit is a multiple of the chunk size
+        }
+        const int base = f.claim_base;
+        f.claim_base += kChunk;
         if (base >= limit) {
             f.drained = true;
         } else {
@@ -514,11 +525,17 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
     uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
     unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
+    float4* s_top = reinterpret_cast<float4*>(s_queue + WARPS * kQueueBytesClosest);  // (v0|id, e1, e2) per root-level primitive
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
         if ((i & 7) != 7)  // the eighth float4 of a node is padding
             reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
+    if (threadIdx.x < kMaxTop) {
+        s_top[threadIdx.x * 3] = top.v0[threadIdx.x];
+        s_top[threadIdx.x * 3 + 1] = top.e1[threadIdx.x];
+        s_top[threadIdx.x * 3 + 2] = top.e2[threadIdx.x];
+    }
     if (lane == 0) {
         mbar_init(&s_bars[warp * 2], 1);
         mbar_init(&s_bars[warp * 2 + 1], 1);
@@ -561,7 +578,8 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
             const float4 o4 = buf[lane], d4 = buf[kChunk + lane];
             const bool live = (f2i(d4.w) & 0xff) == SLOT_ACTIVE;
             const int my_slot = fd.cur_base + (int)lane;
-            TopResult tr = top_closest(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
+            TopResult tr = ph.ranked_top ? top_closest_ranked(top, s_top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), live)
+                                         : top_closest(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z));
             if (live) rays++;
             // decided by the root-level list alone (the winner is verified by the consumer, resolve_hit)
             if (live && !tr.enters) st_cs_f2(&pool.hit[my_slot], make_float2(tr.d_min, i2f(tr.id)));
@@ -903,7 +921,7 @@ int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
 template <int THREADS>
 size_t fast_smem_bytes(int k_smem, bool shadow) {
     const size_t stack = shadow ? (size_t)FastCfg<THREADS>::SS * THREADS * 4 : (size_t)FastCfg<THREADS>::SC * THREADS * 8;
-    return (size_t)k_smem * kSmemNodeStride + stack +
+    return (size_t)k_smem * kSmemNodeStride + stack + (shadow ? 0 : kTopStageBytes) +
            (size_t)(THREADS / 32) * (kStageBytesPerWarp + 16 + (shadow ? kQueueBytesShadow : kQueueBytesClosest));
 }
 

@@ -80,6 +80,7 @@ struct Phases {
     int node_iters;  // node steps per phase at most
     int node_min;    // ... and only while at least this many lanes still have node work
     int tri_min;     // extra triangle steps while at least this many lanes have a triangle waiting
+    int ranked_top;  // closest hit: rank the root-level primitives per lane and test nearest first (top_closest_ranked)
 };
 
 struct LaunchDims {
