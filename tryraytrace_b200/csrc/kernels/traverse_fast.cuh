@@ -313,6 +313,21 @@ TRT_DEV float2 tri_test_pair(const float2 nv0[3], const float2 e1[3], const floa
     return make_float2(ok0 ? t.x : 0.f, ok1 ? t.y : 0.f);
 }
 
+// Two leaf triangles from their records (v0|id, v1, v2): edges, negations and the test, all packed.
+// e1 = v1 - v0 and e2 = v2 - v0 are the reference's single rounded subtractions (:239-240); -v0 and -e1 are
+// exact sign flips (multiplication by -1).
+TRT_DEV float2 tri_test_pair_records(const float4 a0, const float4 b0, const float4 c0, const float4 a1, const float4 b1,
+                                     const float4 c1, const F3 o, const F3 d, const F3 nd) {
+    const float2 v0[3] = {make_float2(a0.x, a1.x), make_float2(a0.y, a1.y), make_float2(a0.z, a1.z)};
+    const float2 e1[3] = {sub2p(make_float2(b0.x, b1.x), v0[0]), sub2p(make_float2(b0.y, b1.y), v0[1]),
+                          sub2p(make_float2(b0.z, b1.z), v0[2])};
+    const float2 e2[3] = {sub2p(make_float2(c0.x, c1.x), v0[0]), sub2p(make_float2(c0.y, c1.y), v0[1]),
+                          sub2p(make_float2(c0.z, c1.z), v0[2])};
+    const float2 nv0[3] = {mul2(v0[0], -1.f), mul2(v0[1], -1.f), mul2(v0[2], -1.f)};
+    const float2 ne1[3] = {mul2(e1[0], -1.f), mul2(e1[1], -1.f), mul2(e1[2], -1.f)};
+    return tri_test_pair(nv0, e1, ne1, e2, o, d, nd);
+}
+
 // Slab interval of one child from its near/far planes (selected by the sign of the inverse
 // direction when the node was loaded), clamped to [lo_clamp, hi_clamp]; `<=` instead of the
 // reference's strict tests only ever adds candidates (superset).
@@ -654,32 +669,44 @@ TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const S
     for (int k = 0; k < 4; k++) push_child<E>(s.np, s.tp, tn[k], tf[k], r[k], key[k], best);
 }
 
+// Triangle step: the next leaf of the triangle stack that can still matter, TWO of its triangles at once
+// (packed FP32, tri_test_pair): most leaves of the SAH tree hold two (C2: 2734 of 3332), so this nearly halves
+// the number of triangle steps.  A leaf with one triangle left tests it twice (second result ignored).
 template <uint32_t E, int S, bool COUNT>
-TRT_DEV void closest_tri_step(const SceneDev& sc, ClosestRay& s, uint32_t base, WideCounts* wc) {
+TRT_DEV void closest_tri_step2(const SceneDev& sc, ClosestRay& s, uint32_t base, WideCounts* wc) {
     const uint32_t ttop = base + (S - 1) * E;
     const float limit = s.d_min * kCullSlack;
     int tri = -1;
+    bool two = false;
     while (s.tp != ttop) {
         const uint32_t top = s.tp + E;
         const uint2 e = lds64(top);
         if (!(__uint_as_float(e.x) < limit)) { s.tp = top; continue; }
         const int code = (int)e.y;
         tri = code >> 2;
-        const bool more = (code & 3) != 0;
-        sts64_if(more, top, e.x, (uint32_t)(code + 3));  // first + 1, count - 1
+        const int left = code & 3;  // triangles after this one
+        two = left != 0;
+        const bool more = left > 1;
+        sts64_if(more, top, e.x, (uint32_t)(code + 6));  // first + 2, count - 2
         if (!more) s.tp = top;
         break;
     }
     if (tri < 0) return;
-    if (COUNT) wc->tris++;
+    if (COUNT) wc->tris += two ? 2 : 1;
     const float4* tp = sc.tris + (size_t)tri * 3;
-    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-    const F3 v0 = f3(ta.x, ta.y, ta.z), v1 = f3(tb.x, tb.y, tb.z), v2 = f3(tc.x, tc.y, tc.z);
-    const float t = tri_test_flat(v0, x_sub(v1, v0), x_sub(v2, v0), s.o, s.d);
-    const int tid = f2i(ta.w);
-    if (t > 0.f && (t < s.d_min || (t == s.d_min && (tid & kTriIdMask) < (s.id & kTriIdMask)))) {
-        s.d_min = t;  // accepted on the triangle test alone; the winner is verified where it is consumed
-        s.id = tid;
+    const float4* tq = tp + (two ? 3 : 0);
+    const float4 a0 = __ldg(tp), b0 = __ldg(tp + 1), c0 = __ldg(tp + 2);
+    const float4 a1 = __ldg(tq), b1 = __ldg(tq + 1), c1 = __ldg(tq + 2);
+    const F3 nd = f3(-s.d.x, -s.d.y, -s.d.z);
+    const float2 t = tri_test_pair_records(a0, b0, c0, a1, b1, c1, s.o, s.d, nd);
+    const int id0 = f2i(a0.w), id1 = f2i(a1.w);
+    if (t.x > 0.f && (t.x < s.d_min || (t.x == s.d_min && (id0 & kTriIdMask) < (s.id & kTriIdMask)))) {
+        s.d_min = t.x;  // accepted on the triangle test alone; the winner is verified where it is consumed
+        s.id = id0;
+    }
+    if (two && t.y > 0.f && (t.y < s.d_min || (t.y == s.d_min && (id1 & kTriIdMask) < (s.id & kTriIdMask)))) {
+        s.d_min = t.y;
+        s.id = id1;
     }
 }
 
@@ -818,6 +845,8 @@ TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const Sc
     push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.w, ay.w), fmaxf(az.w, lo)), fminf(fminf(bx.w, by.w), fminf(bz.w, hi)), n.ch.w);
 }
 
+// one triangle per step (the any-hit kernel keeps this form: the packed pair test needs eight more registers,
+// which takes the room the overlapped regenerate CTAs live in)
 template <uint32_t E, int S, bool COUNT>
 TRT_DEV void shadow_tri_step(const SceneDev& sc, ShadowRay& s, uint32_t base, WideCounts* wc) {
     const uint32_t ttop = base + (S - 1) * E;
@@ -848,6 +877,50 @@ TRT_DEV void shadow_tri_step(const SceneDev& sc, ShadowRay& s, uint32_t base, Wi
             derive_leaf_box(v0, v1, v2, &bmin, &bmax);
             reach = ref_slab(bmin, bmax, s.o, s.inv, 0.001f, s.max_dist);
         }
+        if (reach) s.occluded = true;
+    }
+}
+
+// occluder check of one triangle that the test hit inside the interval: the reference must be able to reach it
+// (the record is read again here, from L1: keeping six vectors live across the packed test spilled)
+TRT_DEV bool shadow_reach(const SceneDev& sc, const ShadowRay& s, const float4* rec) {
+    const float4 ta = __ldg(rec), tb = __ldg(rec + 1), tc = __ldg(rec + 2);
+    if (f2i(ta.w) & kTriNoDerive) {
+        // leaf box not derivable: ask the reference traversal itself (exact, rare)
+        Ray r;
+        r.o = s.o;
+        r.d = s.d;
+        VisitCounts vc = {0, 0, 0};
+        return ref_shadow<false>(sc, r, s.max_dist, &vc);
+    }
+    float4 bmin, bmax;
+    derive_leaf_box(f3(ta.x, ta.y, ta.z), f3(tb.x, tb.y, tb.z), f3(tc.x, tc.y, tc.z), &bmin, &bmax);
+    return ref_slab(bmin, bmax, s.o, s.inv, 0.001f, s.max_dist);
+}
+
+// any hit: two triangles of the leaf per step (see closest_tri_step2)
+template <uint32_t E, int S, bool COUNT>
+TRT_DEV void shadow_tri_step2(const SceneDev& sc, ShadowRay& s, uint32_t base, WideCounts* wc) {
+    const uint32_t ttop = base + (S - 1) * E;
+    if (s.occluded || s.tp == ttop) return;
+    const uint32_t top = s.tp + E;
+    const int scode = (int)lds32(top);
+    const int tri = scode >> 2;
+    const int left = scode & 3;
+    const bool two = left != 0, more = left > 1;
+    sts32_if(more, top, (uint32_t)(scode + 6));
+    if (!more) s.tp = top;
+    if (COUNT) wc->tris += two ? 2 : 1;
+    const float4* tp = sc.tris + (size_t)tri * 3;
+    const float4* tq = tp + (two ? 3 : 0);
+    const float4 a0 = __ldg(tp), b0 = __ldg(tp + 1), c0 = __ldg(tp + 2);
+    const float4 a1 = __ldg(tq), b1 = __ldg(tq + 1), c1 = __ldg(tq + 2);
+    const F3 nd = f3(-s.d.x, -s.d.y, -s.d.z);
+    const float2 t = tri_test_pair_records(a0, b0, c0, a1, b1, c1, s.o, s.d, nd);
+    const bool h0 = t.x > 0.001f && t.x < s.t_hi, h1 = two && t.y > 0.001f && t.y < s.t_hi;
+    if (h0 || h1) {
+        bool reach = h0 && shadow_reach(sc, s, tp);
+        if (!reach && h1) reach = shadow_reach(sc, s, tq);
         if (reach) s.occluded = true;
     }
 }

@@ -628,7 +628,7 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
 #pragma unroll 1
         for (;;) {
             if (COUNT && lane == 0) dbg_tsteps++;
-            closest_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
+            closest_tri_step2<E, S, COUNT>(sc, st, stk_base, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, st.tp != stk_ttop);
             if (__popc(m) < ph.tri_min) break;
         }
