@@ -1,6 +1,6 @@
 """GPU tier: edge cases of the render entry points -- degenerate image sizes, empty jobs, scenes
 without lights or without a tree, tiny pools, light lists longer than the root-level list takes.
-Each case is checked against the unmodified reference kernel (ids exact, radiance PSNR >= 40 dB)."""
+Each case is checked against the unmodified reference kernel (ids exact, radiance PSNR >= 60 dB)."""
 import numpy as np
 import pytest
 import torch
@@ -17,7 +17,7 @@ def ctx(trt):
     c.close()
 
 
-def radiance_gate(trt, ref, ctx, sc, cam, w, h, spp, what, **opt):
+def radiance_gate(trt, ref, ctx, sc, cam, w, h, spp, what, min_psnr=60.0, **opt):
     ctx.upload(sc)
     ref.init_scene(sc)
     n = w * h
@@ -34,7 +34,7 @@ def radiance_gate(trt, ref, ctx, sc, cam, w, h, spp, what, **opt):
     assert np.isfinite(a).all()
     p = psnr_8bit(ref.tonemap(a, spp), ref.tonemap(a_ref.cpu().numpy(), spp))
     print(f"{what}: PSNR {p:.1f} dB")
-    assert p >= 40.0, what
+    assert p >= min_psnr, what
     return a
 
 
@@ -42,7 +42,8 @@ def radiance_gate(trt, ref, ctx, sc, cam, w, h, spp, what, **opt):
 def test_degenerate_image_sizes(trt, ref, ctx, assets, w, h):
     sc = trt.HostScene.from_config(1, assets)
     cam, w, h = trt.config_camera(1, w, h)
-    radiance_gate(trt, ref, ctx, sc, cam, w, h, 8, f"C1 {w}x{h}")
+    # a handful of pixels: one 8-bit level on one of them is already ~50 dB
+    radiance_gate(trt, ref, ctx, sc, cam, w, h, 8, f"C1 {w}x{h}", min_psnr=40.0)
 
 
 def test_zero_frames_is_a_no_op(trt, ctx, assets):
@@ -61,6 +62,18 @@ def test_tiny_pool_and_short_job(trt, ref, ctx, assets):
     cam, w, h = trt.config_camera(2, 320, 180)
     radiance_gate(trt, ref, ctx, sc, cam, w, h, 4, "C2 pool 256", pool_paths=256)
     radiance_gate(trt, ref, ctx, sc, cam, w, h, 1, "C2 one frame")
+
+
+@pytest.mark.parametrize("pool", [33280, 40448, 65024])
+def test_pool_between_the_compaction_floor_and_twice_the_floor(trt, ref, ctx, assets, pool):
+    """Pools of 32 Ki .. 64 Ki slots on a tiny job: the drain compaction clamps its new bound to 32 Ki, so the list
+    of dead slots below the bound can hold almost the whole pool (it used to be sized for half of it and
+    overflowed into neighbouring device memory)."""
+    sc = trt.HostScene.from_config(1, assets)
+    cam, w, h = trt.config_camera(1, 64, 64)
+    radiance_gate(trt, ref, ctx, sc, cam, w, h, 1, f"C1 64x64, pool {pool}", min_psnr=50.0, pool_paths=pool)
+    cam, w, h = trt.config_camera(1, 320, 240)
+    radiance_gate(trt, ref, ctx, sc, cam, w, h, 3, f"C1 320x240, pool {pool}", pool_paths=pool)
 
 
 def test_scene_without_lights(trt, ref, ctx, assets):

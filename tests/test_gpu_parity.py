@@ -109,8 +109,8 @@ def test_fast_primary_ids_match_unmodified_kernel(trt, ref, ctx, scenes, config)
 
 @pytest.mark.parametrize("config", [1, 2])
 def test_secondary_rays_fast_equals_reference_order(trt, ref, ctx, scenes, config):
-    """Incoherent rays from surface points: FAST and REF agree on closest hit (id, t) and on
-    shadow-ray occlusion for every ray."""
+    """Incoherent rays: FAST and REF agree with each other on closest hit (id, t) and on shadow-ray occlusion
+    for every ray (both are checked against the oracle in test_arbitrary_rays_match_the_oracle)."""
     sc, cam, w, h = setup(trt, ref, ctx, scenes, config)
     g = torch.Generator(device="cuda").manual_seed(11 + config)
     n = 400_000
@@ -135,10 +135,70 @@ def test_secondary_rays_fast_equals_reference_order(trt, ref, ctx, scenes, confi
     assert 0.05 < (a[0] >= 0).float().mean() <= 1.0 and 0.0 < a[2].float().mean() < 1.0
 
 
+def _incoherent_rays(n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rays = torch.zeros(n, 8, device="cuda")
+    rays[:, 0] = torch.rand(n, generator=g, device="cuda") * 100
+    rays[:, 1] = torch.rand(n, generator=g, device="cuda") * 100
+    rays[:, 2] = torch.rand(n, generator=g, device="cuda") * 300
+    d = torch.randn(n, 3, generator=g, device="cuda")
+    rays[:, 3:6] = d / d.norm(dim=1, keepdim=True)
+    rays[:, 6] = torch.rand(n, generator=g, device="cuda") * 150 + 1
+    rays[: n // 50, 3] = 0.0  # axis-parallel directions exercise the safe_inv / infinite-reciprocal paths
+    rays[n // 50: n // 25, 4] = 0.0
+    torch.cuda.synchronize()
+    return rays
+
+
+@pytest.mark.parametrize("config", [1, 2, 3, 4])
+def test_arbitrary_rays_match_the_oracle(trt, ref, ctx, scenes, config):
+    """Incoherent closest-hit AND shadow rays, both traversal modes, against the ORACLE (not against each other):
+    closest hit = restatement of reference renderer.cu:371-425 (ids checked against the unmodified kernel above),
+    shadow = the reference's own unmodified __device__ trace_shadow (renderer.cu:273-314).  Bit-exact."""
+    sc, cam, w, h = setup(trt, ref, ctx, scenes, config)
+    n = 400_000
+    rays = _incoherent_rays(n, 23 + config)
+    want_id, want_t, want_occ = dev_zeros(n, torch.int32), dev_zeros(n, torch.float32), dev_zeros(n, torch.int32)
+    ref.trace_rays(rays, n, 0, d_id=want_id, d_t=want_t)
+    ref.trace_rays(rays, n, 1, d_occ=want_occ)
+    assert 0.05 < (want_id >= 0).float().mean() <= 1.0 and 0.0 < want_occ.float().mean() < 1.0
+    for mode in (trt.TRAVERSE_REF, trt.TRAVERSE_FAST):
+        i, t, o = dev_zeros(n, torch.int32), dev_zeros(n, torch.float32), dev_zeros(n, torch.int32)
+        ctx.trace_closest(rays, n, mode, i, t)
+        ctx.trace_shadow(rays, n, mode, o)
+        bad_id = int((i != want_id).sum())
+        hit = want_id >= 0
+        bad_t = int((t.view(torch.int32)[hit] != want_t.view(torch.int32)[hit]).sum())
+        bad_occ = int((o != want_occ).sum())
+        print(f"config {config} mode {mode}: id mismatches {bad_id}, d_min mismatches {bad_t}, occlusion mismatches {bad_occ}")
+        assert bad_id == 0, "closest-hit ids differ from the oracle"
+        assert bad_t == 0, "closest-hit distances differ from the oracle"
+        assert bad_occ == 0, "shadow-ray occlusion differs from the reference's trace_shadow"
+
+
+@pytest.mark.parametrize("config", [3, 4])
+def test_fast_primary_ids_at_the_named_resolution(trt, ref, ctx, scenes, config):
+    """Frame 1 of C3 (1920x1080) and C4 (3840x2160) at the resolution BASELINE.json names: first-hit ids of the
+    fast path equal the unmodified kernel's on every pixel."""
+    sc = scenes.get(config)
+    ctx.upload(sc)
+    ref.init_scene(sc)
+    cam, w, h = trt.config_camera(config)
+    n = w * h
+    want = ref.first_hit_ids(w, h, 1, cam)
+    ids = dev_zeros(n, torch.int32)
+    ctx.trace_primary(w, h, 1, cam, trt.TRAVERSE_FAST, d_id=ids)
+    bad = int((ids.cpu().numpy() != want).sum())
+    print(f"config {config} {w}x{h}: id mismatches {bad} of {n}")
+    assert bad == 0
+
+
 @pytest.mark.parametrize("config,mode", [(1, "ref"), (1, "fast"), (2, "fast"), (3, "fast")])
 def test_radiance_same_stream_gate(trt, ref, ctx, scenes, config, mode):
-    """Same seeds, same spp: PSNR >= 40 dB on the tone-mapped 8-bit image against the unmodified
-    reference kernel (gate (i)), and the image means agree to 0.5%."""
+    """Same seeds, same spp, against the unmodified reference kernel (SURVEY 8d gate (i), tightened to what is
+    measured): PSNR >= 80 dB on the tone-mapped 8-bit image (SURVEY asks for 40), at least 99.9 % of the linear
+    radiance values within 1e-4 (relative, floor 1), image means within 0.1 %.  Differences can only come from
+    FP re-association in shading, the summation order of the accumulate, and the rare decision flips they cause."""
     sc, cam, w, h = setup(trt, ref, ctx, scenes, config)
     spp = 16
     acc_ref, stage = dev_zeros(w * h * 4, torch.float32), dev_zeros(w * h * 4, torch.float32)
@@ -155,8 +215,47 @@ def test_radiance_same_stream_gate(trt, ref, ctx, scenes, config, mode):
     rel = np.abs(a.mean(0) - b.mean(0)) / np.maximum(b.mean(0), 1e-6)
     frac_equal = np.mean(np.abs(a - b) <= 1e-4 * np.maximum(np.abs(b), 1.0))
     print(f"config {config} {mode}: PSNR {p:.2f} dB, mean rel err {rel}, values within 1e-4: {frac_equal:.6f}")
-    assert p >= 40.0
-    assert (rel < 5e-3).all()
+    assert p >= 80.0
+    assert frac_equal >= 0.999
+    assert (rel < 1e-3).all()
+
+
+@pytest.mark.parametrize("config,w,h,n_spp,ref_spp", [(1, 320, 240, 64, 4096), (2, 480, 270, 64, 2048)])
+def test_radiance_estimator_gate(trt, ref, ctx, scenes, config, w, h, n_spp, ref_spp):
+    """SURVEY 8d gate (ii), valid whatever the RNG streams: with R_inf = the unmodified kernel at ref_spp (disjoint
+    seeds), MSE(ours@N, R_inf) <= 1.1 x MSE(reference@N with other seeds, R_inf) on linear radiance, and the
+    per-channel mean of the whole image within 0.5 % of R_inf's (a mis-reproduced estimator quirk shows up as bias).
+    The MSE of a 64-spp path-traced image is itself a noisy, firefly-dominated statistic (two reference runs with
+    different seeds differ by tens of percent), so radiance is clamped at 4 for the MSE and the reference side is the
+    largest of three independent runs."""
+    sc = scenes.get(config)
+    ctx.upload(sc)
+    ref.init_scene(sc)
+    cam, w, h = trt.config_camera(config, w, h)
+    n = w * h
+    stage = dev_zeros(n * 4, torch.float32)
+
+    def reference(first, spp):
+        a = dev_zeros(n * 4, torch.float32)
+        ref.render_frames(a, stage, w, h, first, spp, cam, cadence=0)
+        return a.cpu().numpy().reshape(-1, 4)[:, :3].astype(np.float64) / spp
+
+    r_inf = reference(100_001, ref_spp)
+    ours = dev_zeros(n * 4, torch.float32)
+    ctx.render(ours, w, h, 1, n_spp, cam, trt.default_opts(pool_paths=1 << 18))
+    ctx.synchronize()
+    ours = ours.cpu().numpy().reshape(-1, 4)[:, :3].astype(np.float64) / n_spp
+
+    def mse(a):
+        return float(np.mean((np.minimum(a, 4.0) - np.minimum(r_inf, 4.0)) ** 2))
+
+    mse_ours = mse(ours)
+    mse_refs = [mse(reference(1 + k * n_spp, n_spp)) for k in (1, 2, 3)]
+    bias = np.abs(ours.mean(0) - r_inf.mean(0)) / np.maximum(r_inf.mean(0), 1e-9)
+    print(f"config {config}: MSE ours {mse_ours:.6g} reference runs {[f'{m:.6g}' for m in mse_refs]} "
+          f"ratio to the largest {mse_ours / max(mse_refs):.4f}, mean rel err {bias}")
+    assert mse_ours <= 1.1 * max(mse_refs)
+    assert (bias <= 5e-3).all()
 
 
 def test_render_matches_instrumented_ray_counts(trt, ref, ctx, scenes):

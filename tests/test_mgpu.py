@@ -41,6 +41,8 @@ def test_mgpu_library_exports_the_header_and_the_c_host_links():
 def test_multi_gpu_pass_equals_single_gpu_pass(assets):
     import torch
     n = max(1, min(torch.cuda.device_count(), 8))
+    if "TRT_EXPECT_GPUS" in os.environ:  # multi-GPU boxes: the driver of the run states how many it handed out
+        assert n == int(os.environ["TRT_EXPECT_GPUS"]), f"expected {os.environ['TRT_EXPECT_GPUS']} GPUs, see {n}"
     b = build_host() if not BIN.exists() else BIN
     # single node: keep NCCL's bootstrap off the network interfaces it would otherwise probe
     env = dict(os.environ, LD_LIBRARY_PATH=f"{LIBDIR}:{os.environ.get('LD_LIBRARY_PATH', '')}", NCCL_SOCKET_IFNAME="lo",
@@ -53,3 +55,5 @@ def test_multi_gpu_pass_equals_single_gpu_pass(assets):
         d = json.loads(lines[-1])
         print(d)
         assert d["n_gpus"] == n and d["max_rel_diff"] < 1e-5 and d["sum_multi"] > 0
+        if torch.cuda.device_count() > 1:
+            assert d["n_gpus"] > 1, "more than one GPU is visible but the pass ran on one"

@@ -255,7 +255,9 @@ int ensure_pool(trt_ctx* c, int cap) {
     c->d_compact = nullptr;
     c->pool_cap = 0;
     if (int rc = alloc_pool(cap, true, &c->pool_mem, &c->pool, &c->d_free)) return rc;
-    CU(cudaMalloc(&c->d_compact, ((size_t)cap + 1024) * sizeof(int)));
+    // two lists of up to cap entries each (live slots beyond the new bound / dead slots below it; the bound is
+    // clamped to kCompactMinCap, so with a small pool the dead list can hold nearly the whole pool)
+    CU(cudaMalloc(&c->d_compact, 2 * ((size_t)cap + 512) * sizeof(int)));
     c->pool_cap = cap;
     return 0;
 }
@@ -550,15 +552,8 @@ void trt_default_opts(trt_opts* o) {
     o->count_rays = 0;
 }
 
-int trt_create(int device, trt_ctx** out) {
-    if (!out) return fail(TRT_ERR_ARG, "null out pointer");
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-        cudaGetLastError();
-        return fail(TRT_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
-    }
-    if (device < 0 || device >= n) return fail(TRT_ERR_ARG, "device %d out of range (have %d)", device, n);
-    trt_ctx* c = new trt_ctx();
+namespace {
+int init_ctx(trt_ctx* c, int device) {
     c->device = device;
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
@@ -581,6 +576,25 @@ int trt_create(int device, trt_ctx** out) {
     CU(cudaMalloc(&c->d_ctl, sizeof(Control)));
     CU(cudaMemset(c->d_ctl, 0, sizeof(Control)));
     CU(cudaMallocHost(&c->h_ctl, 2 * sizeof(Control)));
+    return 0;
+}
+}  // namespace
+
+int trt_create(int device, trt_ctx** out) {
+    if (!out) return fail(TRT_ERR_ARG, "null out pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TRT_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    }
+    if (device < 0 || device >= n) return fail(TRT_ERR_ARG, "device %d out of range (have %d)", device, n);
+    trt_ctx* c = new trt_ctx();
+    if (int rc = init_ctx(c, device)) {  // a half-built context is torn down again (message kept)
+        const std::string keep = g_err;
+        trt_destroy(c);
+        g_err = keep;
+        return rc;
+    }
     *out = c;
     return 0;
 }
@@ -588,7 +602,7 @@ int trt_create(int device, trt_ctx** out) {
 int trt_destroy(trt_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     free_scene(c);
     cudaFree(c->d_row_a);
     cudaFree(c->d_row_b);
@@ -598,17 +612,14 @@ int trt_destroy(trt_ctx* c) {
     cudaFree(c->d_compact);
     cudaFree(c->scratch_mem);
     cudaFree(c->d_ctl);
-    cudaFreeHost(c->h_ctl);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
     cudaFree(c->d_accum_own);
     for (cudaEvent_t e : c->marks) cudaEventDestroy(e);
-    cudaEventDestroy(c->ev_begin);
-    cudaEventDestroy(c->ev_end);
-    cudaEventDestroy(c->ev_poll[0]);
-    cudaEventDestroy(c->ev_poll[1]);
-    cudaEventDestroy(c->ev_fork);
-    cudaEventDestroy(c->ev_join);
-    cudaStreamDestroy(c->side_stream);
-    cudaStreamDestroy(c->own_stream);
+    for (cudaEvent_t e : {c->ev_begin, c->ev_end, c->ev_poll[0], c->ev_poll[1], c->ev_fork, c->ev_join})
+        if (e) cudaEventDestroy(e);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    cudaGetLastError();
     delete c;
     return 0;
 }

@@ -53,10 +53,19 @@ int trt_mgpu_create(int n_gpus, const int* devices, trt_mgpu** out) {
     m->streams.assign(n_gpus, nullptr);
     m->comms.assign(n_gpus, nullptr);
     for (int g = 0; g < n_gpus; g++) {
-        if (int rc = trt_create(m->devices[g], &m->ctx[g])) return mfail("trt_create", trt_last_error()), rc;
+        if (int rc = trt_create(m->devices[g], &m->ctx[g])) {
+            mfail("trt_create", trt_last_error());
+            trt_mgpu_destroy(m);  // the contexts created so far
+            return rc;
+        }
         m->streams[g] = (cudaStream_t)trt_stream(m->ctx[g]);
     }
-    MNCCL(ncclCommInitAll(m->comms.data(), n_gpus, m->devices.data()));
+    if (ncclResult_t r = ncclCommInitAll(m->comms.data(), n_gpus, m->devices.data()); r != ncclSuccess) {
+        mfail("ncclCommInitAll", ncclGetErrorString(r));
+        for (auto& cm : m->comms) cm = nullptr;
+        trt_mgpu_destroy(m);
+        return TRT_ERR_NCCL;
+    }
     *out = m;
     return 0;
 }
@@ -90,6 +99,7 @@ int trt_mgpu_render_to_host(trt_mgpu* m, float* h_accum, int width, int height, 
     const int G = (int)m->ctx.size();
     const size_t bytes = (size_t)width * height * 16;
     if (bytes != m->accum_bytes) {
+        m->accum_bytes = 0;  // stays 0 if an allocation below fails, so the next call allocates again
         for (int g = 0; g < G; g++) {
             MCU(cudaSetDevice(m->devices[g]));
             cudaFree(m->accum[g]);

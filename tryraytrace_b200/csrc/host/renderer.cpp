@@ -33,19 +33,27 @@ void init_scene_data(const std::vector<Object>& objects, const std::vector<std::
                      const std::vector<LinearBVHNode>& nodes, const std::vector<int>& light_indices) {
     trt_ctx* c = global_ctx();
     if (!c) return;
+    // Texture slot i belongs to texture_files[i] (objects name it by tex_id).  A file that fails to load keeps
+    // its slot -- the reference stores a null handle there (src/renderer.cu:97-126) -- so later indices do not
+    // shift: the slot gets a 1x1 placeholder and exactly the objects that named it fall back to untextured.
+    static const unsigned char kWhite[3] = {255, 255, 255};
     std::vector<trt_image> imgs;
     std::vector<unsigned char*> owned;
+    std::vector<bool> failed;
     for (const std::string& f : texture_files) {
         int w = 0, h = 0;
         unsigned char* rgb = load_ppm(f.c_str(), &w, &h);
-        if (!rgb) continue;  // the reference leaves a null handle; here the texture slot is dropped
-        owned.push_back(rgb);
-        imgs.push_back(trt_image{w, h, rgb});
+        failed.push_back(rgb == nullptr);
+        if (rgb) {
+            owned.push_back(rgb);
+            imgs.push_back(trt_image{w, h, rgb});
+        } else {
+            imgs.push_back(trt_image{1, 1, kWhite});
+        }
     }
-    // objects that name a texture that failed to load fall back to untextured
     std::vector<Object> objs = objects;
     for (Object& o : objs)
-        if (o.tex_id >= (int)imgs.size()) o.tex_id = -1;
+        if (o.tex_id >= (int)imgs.size() || (o.tex_id >= 0 && failed[o.tex_id])) o.tex_id = -1;
     if (trt_upload_scene(c, objs.data(), (int)objs.size(), nodes.data(), (int)nodes.size(), light_indices.data(),
                          (int)light_indices.size(), imgs.data(), (int)imgs.size()) != 0)
         std::fprintf(stderr, "[Renderer Error] %s\n", trt_last_error());

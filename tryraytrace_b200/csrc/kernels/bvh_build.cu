@@ -683,9 +683,16 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
     max_leaf = std::max(1, std::min(4, max_leaf));
     *out = DeviceWideBvh();
     Scratch tmp(s);
-    cudaEvent_t ev0, ev1;
-    BCU(cudaEventCreate(&ev0));
-    BCU(cudaEventCreate(&ev1));
+    struct Events {  // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() {
+            if (a) cudaEventDestroy(a);
+            if (b) cudaEventDestroy(b);
+        }
+    } evs;
+    BCU(cudaEventCreate(&evs.a));
+    BCU(cudaEventCreate(&evs.b));
+    const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
     BCU(cudaEventRecord(ev0, s));
 
     float4 *olo, *ohi;
@@ -971,8 +978,6 @@ int build_wide_bvh_device(const float4* d_objects, int n, const float4* d_ref_no
     tp.root_lo = make_float4(h_root[0].x, h_root[0].y, h_root[0].z, 0.f);
     tp.root_hi = make_float4(h_root[1].x, h_root[1].y, h_root[1].z, 0.f);
     BCU(cudaEventElapsedTime(&out->build_ms, ev0, ev1));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     BCU(cudaGetLastError());
     return 0;
 }

@@ -1078,7 +1078,7 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
     }
     if (compact_lists && visit > kCompactMinCap) {  // the host launches these only once the job is close to its drain phase
         int* list_a = compact_lists;
-        int* list_b = compact_lists + pool.capacity / 2 + 512;
+        int* list_b = compact_lists + pool.capacity + 512;  // each list is sized for the whole pool
         k_compact_scan<<<dims.sms * 2, 1024, 0, s>>>(pool, ctl, list_a, list_b);
         k_compact_move<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b);
         k_compact_commit<<<1, 32, 0, s>>>(ctl);
