@@ -14,8 +14,14 @@ HOST_SRC  := loader bvh scene camera image_io pipeline renderer xorwow_tables wi
 HOST_OBJS := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(HOST_SRC)))
 CU_OBJS   := $(OBJDIR)/wavefront.o $(OBJDIR)/bvh_build.o $(OBJDIR)/trt_capi.o
 
-.PHONY: all lib oracle assets clean
-all: lib oracle assets
+.PHONY: all lib oracle assets clean peaks
+all: lib oracle assets peaks
+
+# machine-peak microbenchmarks for the roofline (FP32 FMA rate, L2-resident read bandwidth); bench.py runs it
+peaks: build/peaks
+build/peaks: tools/peaks.cu
+	@mkdir -p build
+	$(NVCC) -O3 $(ARCH) -o $@ $<
 
 lib: $(LIBDIR)/libtrt_b200.so $(LIBDIR)/libtrt_b200_mgpu.so
 

@@ -142,3 +142,43 @@ def full_counts(d_accum, w, h, first, n, cam, max_depth=30, rr_threshold=3, seed
     rc = ref().ref_full_counts(_dp(d_accum), w, h, seed_base, first, n, _p(cam), max_depth, rr_threshold, _p(tot))
     assert rc == 0
     return dict(closest_rays=int(tot[0]), shadow_rays=int(tot[1]), nodes_fetched=int(tot[2]), nodes_entered=int(tot[3]), tris_tested=int(tot[4]))
+
+
+# ---- scenes built with the reference's own host code only (no product library involved) ------------
+class ReferenceScene:
+    """BASELINE config C2 / C4 assembled the way reference src/main.cpp:79-101 does, through the reference's
+    own create_cornell_box (room shell), load_obj and BVH::build compiled into oracle/_ref: what the
+    `--impl reference` arm of bench.py renders.  Byte-identical to tryraytrace_b200.HostScene.from_config
+    (tests/test_host_surface.py checks that)."""
+
+    MESH = {2: ("teapot.obj", (48.0, 5.0, 80.0), 14.0), 4: ("pumpkin.obj", (51.6, 29.5, 146.0), 0.6)}
+    CAMERA = {2: ((50.0, 45.0, 230.0), 60.0, 1920, 1080), 4: ((50.0, 45.0, 230.0), 60.0, 3840, 2160)}
+
+    def __init__(self, config, OBJECT, NODE, asset_dir=None):
+        import os
+        if config not in self.MESH:
+            raise ValueError("reference scenes are built for C2 and C4")
+        asset_dir = Path(asset_dir) if asset_dir else ROOT / "assets"
+        L = ref()
+        buf = np.zeros(8192, dtype=OBJECT)
+        cwd = os.getcwd()
+        os.chdir(asset_dir.parent)  # create_cornell_box reads "assets/teapot.obj" relative to the working directory
+        try:
+            n = L.ref_create_cornell(_p(buf), len(buf), None, 0)
+        finally:
+            os.chdir(cwd)
+        assert n >= 7
+        shell = buf[:7].copy()
+        shell["tex_id"] = -1  # the back wall is untextured outside C3 (SURVEY 8d)
+        name, offset, scale = self.MESH[config]
+        mesh = load_obj(OBJECT, asset_dir / name, offset, scale, (0.75, 0.75, 0.75), 0.0, 1.0)
+        self.objects, self.nodes = bvh_build(OBJECT, NODE, np.concatenate([shell, mesh]))
+        e = self.objects["emission"]
+        self.lights = np.nonzero((e["x"] > 0.1) | (e["y"] > 0.1) | (e["z"] > 0.1))[0].astype(np.int32)  # src/main.cpp:88-96
+        self.texture_files = []
+
+    @classmethod
+    def camera(cls, config, CAMERA, width=None, height=None):
+        pos, pitch_units, w, h = cls.CAMERA[config]
+        w, h = width or w, height or h
+        return camera_params(CAMERA, pos, 0.0, pitch_units, w, h), w, h

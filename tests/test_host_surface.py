@@ -186,3 +186,18 @@ def test_ppm_roundtrip(trt, tmp_path):
     bad.write_bytes(b"P5\n2 2\n255\n0000")
     with pytest.raises(trt.TrtError):
         trt.load_ppm(bad)
+
+
+@pytest.mark.parametrize("config", [2, 4])
+def test_reference_only_scene_equals_the_library_scene(trt, ref, assets, config):
+    """bench.py --impl reference builds its scene with the reference's compiled host code alone
+    (reflib.ReferenceScene: create_cornell_box shell, load_obj, BVH::build); it is the same scene, byte for byte,
+    as the one the library arm renders."""
+    theirs = ref.ReferenceScene(config, trt.OBJECT, trt.NODE, assets)
+    mine = trt.HostScene.from_config(config, assets)
+    assert canon(theirs.objects) == canon(mine.objects)
+    assert theirs.nodes.tobytes() == mine.nodes.tobytes()
+    assert list(theirs.lights) == list(mine.lights)
+    cam_t, w, h = ref.ReferenceScene.camera(config, trt.CAMERA)
+    cam_m, w2, h2 = trt.config_camera(config)
+    assert (w, h) == (w2, h2) and canon(np.asarray(cam_t)) == canon(np.asarray(cam_m))

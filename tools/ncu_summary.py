@@ -17,7 +17,7 @@ want = [("gpu__time_duration.sum", "time"), ("launch__registers_per_thread", "re
         ("l1tex__t_sector_hit_rate.pct", "l1_hit%"), ("lts__t_sector_hit_rate.pct", "l2_hit%"),
         ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex%"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
-        ("lts__t_bytes.sum", "l2_bytes"),
+        ("lts__t_sectors.sum", "l2_sectors(32B)"),
         ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
         ("smsp__warps_eligible.avg.per_cycle_active", "eligible"),
         ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long_sb"),

@@ -41,8 +41,14 @@ if rep.exists():
                 v = float(d[idx[name]].replace(",", ""))
                 u = units[idx[name]]
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
-            tr.append(b("dram__bytes_read.sum") + b("dram__bytes_write.sum"))
+            tr.append((b("dram__bytes_read.sum") + b("dram__bytes_write.sum"), float(d[idx["lts__t_sectors.sum"]].replace(",", "")) * 32.0,
+                       float(d[idx["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(units[idx["gpu__time_duration.sum"]], 1e-6)))
     if tr:
-        (out / "traffic.json").write_text(json.dumps({"k_extend_fast_dram_bytes_per_launch": sum(tr) / len(tr),
-                                                      "launches_sampled": len(tr), "source": f"profiles/{tag}_ncu_full_summary.txt"}))
-        print("traffic", sum(tr) / len(tr))
+        n = len(tr)
+        (out / "traffic.json").write_text(json.dumps({
+            "k_extend_fast_dram_bytes_per_launch": sum(t[0] for t in tr) / n,
+            "k_extend_fast_l2_bytes_per_launch": sum(t[1] for t in tr) / n,
+            "k_extend_fast_ms_under_ncu": sum(t[2] for t in tr) / n,
+            "launches_sampled": n, "what": "full-pool (32 Mi slots) launches of one 64-spp C2 step, ncu --set full",
+            "source": f"profiles/{tag}_ncu_full_summary.txt"}))
+        print("traffic", tr)

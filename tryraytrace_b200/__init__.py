@@ -26,17 +26,8 @@ ASSET_DIR = REPO_ROOT / "assets"
 TRAVERSE_FAST = 0
 TRAVERSE_REF = 1
 
-# ---- record layouts -------------------------------------------------
-VEC = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("_", "<f4")])
-OBJECT = np.dtype([
-    ("v0", VEC), ("v1", VEC), ("v2", VEC), ("albedo", VEC), ("emission", VEC),
-    ("metallic", "<f4"), ("roughness", "<f4"), ("ior", "<f4"), ("transmission", "<f4"),
-    ("tex_id", "<i4"), ("pad1", "<f4"), ("pad2", "<f4"), ("pad3", "<f4"),
-])
-NODE = np.dtype([("min", VEC), ("max", VEC), ("a", "<i4"), ("b", "<i4"), ("axis", "<i4"), ("is_leaf", "<i4")])
-CAMERA = np.dtype([("pos", VEC), ("cx", VEC), ("cy", VEC), ("dir", VEC),
-                   ("lens_radius", "<f4"), ("focus_dist", "<f4"), ("_p", "<f4", (2,))])
-assert OBJECT.itemsize == 112 and NODE.itemsize == 48 and CAMERA.itemsize == 80 and VEC.itemsize == 16
+# ---- record layouts: tryraytrace_b200/records.py (importable without the library) --------
+from .records import VEC, OBJECT, NODE, CAMERA  # noqa: E402,F401
 
 
 BUILD_AUTO, BUILD_HOST_SAH, BUILD_DEVICE_LBVH = 0, 1, 2
