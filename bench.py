@@ -298,7 +298,9 @@ def strong_scaling_block(trt, ctx, args, dist, rank, world, stream):
         host.copy_(acc, non_blocking=True)
         torch.cuda.synchronize()
 
-    sharded_pass(1, 16 * world)  # warm-up (pool allocation, RNG tables for this resolution, NCCL channels)
+    # warm-up with the shape of the timed pass (pool and table allocations for this resolution and frame count,
+    # NCCL's buffers for this message size)
+    sharded_pass(100_001, spp)
     barrier()
     ctx.reset_counters()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -309,6 +311,7 @@ def strong_scaling_block(trt, ctx, args, dist, rank, world, stream):
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     dev_ms = ev0.elapsed_time(ev1)
+    render_ms = ctx.last_render_ms()  # this rank's kernels alone
     c = ctx.counters()
     t = torch.tensor([wall_ms, dev_ms, float(c["closest_rays"] + c["shadow_rays"])], device="cuda", dtype=torch.float64)
     if dist is not None:
@@ -322,7 +325,8 @@ def strong_scaling_block(trt, ctx, args, dist, rank, world, stream):
     if rank == 0:
         block = {"workload": f"C4 room+pumpkin.obj ({len(scene.objects)} triangles) {w}x{h}, {spp} spp in total, "
                              f"sample-sharded over {world} GPU(s)", "n_gpus": world, "spp_total": spp,
-                 "ms": wall_ms, "device_ms": dev_ms, "mrays_per_s": rays / (wall_ms * 1e-3) / 1e6,
+                 "ms": wall_ms, "device_ms": dev_ms, "rank0_render_ms": render_ms,
+                 "mrays_per_s": rays / (wall_ms * 1e-3) / 1e6,
                  "timed_region": "clear + render of this rank's frames + one all-reduce of the accumulation buffer "
                                  "+ D2H of the reduced image to pinned memory + sync; max over ranks",
                  "allreduce_bytes": pixels * 16 if world > 1 else 0, "d2h_bytes": pixels * 16}
