@@ -1,7 +1,8 @@
 // pipeline.h -- display pipeline.  Drop-in for the reference's include/pipeline.h
-// (:11-33 Pipeline, :38-48 API).  The worker thread copies the staging buffer
-// D2H and tone-maps; the tone-map runs on the device so only 4 B/pixel have to
-// cross PCIe when the caller does not need h_accum.
+// (:11-33 Pipeline, :38-48 API).  The worker thread tone-maps the staging buffer ON THE
+// DEVICE (its own stream), copies the 4-byte ARGB pixels to pixel_buffer and reports the
+// frame ready; the float copy into h_accum (16 B/pixel, what the reference's snapshot key
+// reads) follows behind the displayed frame and can be switched off.
 #pragma once
 #include <thread>
 #include <atomic>
@@ -34,3 +35,10 @@ void pipeline_init(Pipeline* pipe, Vec* h_accum, Vec* d_staging, uint32_t* pixel
 bool pipeline_try_dispatch(Pipeline* pipe, int current_gpu_frame);
 bool pipeline_check_frame_ready(Pipeline* pipe);
 void pipeline_destroy(Pipeline* pipe);
+
+// Additions (not in the reference).  The reference worker always copies the float image to
+// h_accum (src/pipeline.cpp:45); a caller that never reads h_accum switches that copy off and the
+// worker then moves exactly 4 bytes per pixel per displayed frame.
+void pipeline_set_host_accum(Pipeline* pipe, bool enabled);
+unsigned long long pipeline_d2h_bytes(Pipeline* pipe);    // device-to-host bytes the worker has copied so far
+unsigned long long pipeline_frames_done(Pipeline* pipe);  // frames the worker has completed

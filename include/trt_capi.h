@@ -176,6 +176,10 @@ int trt_rng_states(trt_ctx* ctx, int width, int height, int frame_seed, int seed
 int trt_tonemap(trt_ctx* ctx, const float* d_accum, int width, int height, int frames,
                 uint32_t* d_argb);
 
+/* The same kernel without a context, on a caller-owned stream of the CURRENT device (the display
+ * worker of include/pipeline.h runs it on its own stream, beside the renderer). */
+int trt_tonemap_stream(const float* d_accum, int n_pixels, int frames, uint32_t* d_argb, void* cuda_stream);
+
 int trt_synchronize(trt_ctx* ctx);
 int trt_get_counters(trt_ctx* ctx, trt_counters* out);
 int trt_reset_counters(trt_ctx* ctx);

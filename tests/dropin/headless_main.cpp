@@ -5,7 +5,8 @@
 //   per frame: launch_render_kernel, device-to-device snapshot, cudaDeviceSynchronize,
 //   pipeline_try_dispatch / pipeline_check_frame_ready -> save raw accumulation + ARGB image.
 // All CUDA calls here are on the legacy default stream, exactly like the reference's.
-// usage: headless_main <asset_dir> <config> <width> <height> <frames> <out_prefix>
+// usage: headless_main <asset_dir> <config> <width> <height> <frames> <out_prefix> [noaccum]
+// noaccum: the caller does not read h_accum (pipeline_set_host_accum(false)): 4 bytes per pixel per displayed frame
 #include "bvh.h"
 #include "camera.h"
 #include "pipeline.h"
@@ -17,6 +18,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -47,6 +49,8 @@ int main(int argc, char** argv) {
     std::vector<uint32_t> pixels(n);
     Pipeline pipe;
     pipeline_init(&pipe, h_accum, d_staging, pixels.data(), width, height);  // main.cpp:139
+    const bool no_accum = argc > 7 && std::string(argv[7]) == "noaccum";
+    if (no_accum) pipeline_set_host_accum(&pipe, false);
 
     int shown = 0;
     for (int gpu_frame = 1; gpu_frame <= frames; gpu_frame++) {  // main.cpp:152-223
@@ -57,9 +61,14 @@ int main(int argc, char** argv) {
         pipeline_try_dispatch(&pipe, gpu_frame);                                      // :198
         if (pipeline_check_frame_ready(&pipe)) shown++;                               // :203
     }
-    // let the worker finish the last frame it took, then show what the window would show
-    for (int spin = 0; spin < 2000 && !pipeline_check_frame_ready(&pipe) && shown == 0; spin++)
-        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    // The worker may still be busy with an earlier snapshot.  A dispatch is accepted only when it is idle, so
+    // once a SECOND dispatch of the final snapshot has been accepted the first one is through (pixels and float
+    // copy), and once a third has been accepted the ARGB image is certainly the final frame's (all three
+    // process the same staging contents).  pipeline_destroy joins the last one.
+    for (int round = 0, spin = 0; round < 3; round++)
+        while (!pipeline_try_dispatch(&pipe, frames) && spin++ < 20000) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    if (pipeline_check_frame_ready(&pipe)) shown++;
+    std::printf("pipeline: frames_done %llu d2h_bytes %llu shown %d\n", pipeline_frames_done(&pipe), pipeline_d2h_bytes(&pipe), shown);
     std::vector<Vec> host(n);
     cudaMemcpy(host.data(), d_accum, n * sizeof(Vec), cudaMemcpyDeviceToHost);
     pipeline_destroy(&pipe);
@@ -67,6 +76,12 @@ int main(int argc, char** argv) {
     if (!f) return 4;
     std::fwrite(host.data(), sizeof(Vec), n, f);
     std::fclose(f);
+    if (!no_accum) {  // what the snapshot key would save (main.cpp:161, :224)
+        f = std::fopen((prefix + ".haccum").c_str(), "wb");
+        if (!f) return 4;
+        std::fwrite(h_accum, sizeof(Vec), n, f);
+        std::fclose(f);
+    }
     f = std::fopen((prefix + ".argb").c_str(), "wb");
     if (!f) return 4;
     std::fwrite(pixels.data(), 4, n, f);

@@ -31,7 +31,8 @@ def test_headless_main_compiles_and_links_against_the_drop_in_headers(trt):
     b = build_headless()
     assert b.exists()
     out = subprocess.run(["nm", "-D", "--undefined-only", str(b)], capture_output=True, text=True).stdout
-    for sym in ("init_scene_data", "launch_render_kernel", "pipeline_init", "pipeline_try_dispatch", "BVH5build"):
+    for sym in ("init_scene_data", "launch_render_kernel", "pipeline_init", "pipeline_try_dispatch", "BVH5build",
+                "pipeline_set_host_accum", "pipeline_d2h_bytes"):
         assert sym in out, f"{sym} is not resolved from libtrt_b200.so"
 
 
@@ -40,7 +41,7 @@ def test_headless_main_compiles_and_links_against_the_drop_in_headers(trt):
 def test_headless_main_matches_the_reference_kernel(trt, ref, assets, tmp_path, config):
     import torch
     from gpu_common import dev_zeros, psnr_8bit
-    b = build_headless() if not BIN.exists() else BIN
+    b = build_headless()
     w, h, frames = 320, 200, 6
     prefix = tmp_path / f"c{config}"
     env = dict(os.environ, LD_LIBRARY_PATH=f"{LIBDIR}:{os.environ.get('LD_LIBRARY_PATH', '')}")
@@ -60,3 +61,31 @@ def test_headless_main_matches_the_reference_kernel(trt, ref, assets, tmp_path, 
     print(f"drop-in main loop, config {config}: PSNR {p:.1f} dB against the reference kernel")
     assert p >= 40.0
     assert (argb >> 24 == 255).all() and len(np.unique(argb)) > 16  # the display worker produced an image
+    # the worker tone-maps on the device (reference src/pipeline.cpp:59-71 on the host): its ARGB image is
+    # toInt(accum / frames) of the final snapshot, and h_accum holds that snapshot for the snapshot key
+    assert (argb != ref.tonemap(acc, frames)).mean() < 1e-5  # packed ARGB8888, reference src/pipeline.cpp:70
+    hacc = np.fromfile(str(prefix) + ".haccum", dtype=np.float32)
+    assert np.array_equal(hacc.reshape(-1, 4)[:, :3], acc.reshape(-1, 4)[:, :3])
+    done, d2h = _pipeline_stats(r.stdout)
+    assert done >= 3 and done * 20 * w * h - 16 * w * h <= d2h <= done * 20 * w * h
+
+
+def _pipeline_stats(stdout):
+    line = [l for l in stdout.splitlines() if l.startswith("pipeline:")][0].split()
+    return int(line[2]), int(line[4])
+
+
+@pytest.mark.gpu
+def test_display_worker_moves_four_bytes_per_pixel_when_h_accum_is_not_wanted(trt, ref, assets, tmp_path):
+    b = build_headless()
+    w, h, frames = 320, 200, 4
+    prefix = tmp_path / "noaccum"
+    env = dict(os.environ, LD_LIBRARY_PATH=f"{LIBDIR}:{os.environ.get('LD_LIBRARY_PATH', '')}")
+    r = subprocess.run([str(b), str(assets), "1", str(w), str(h), str(frames), str(prefix), "noaccum"],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "headless ok" in r.stdout, r.stdout[-400:] + r.stderr[-400:]
+    done, d2h = _pipeline_stats(r.stdout)
+    assert done >= 3 and d2h == done * 4 * w * h  # D2H bytes = 4 * w * h per displayed frame
+    acc = np.fromfile(str(prefix) + ".accum", dtype=np.float32)
+    argb = np.fromfile(str(prefix) + ".argb", dtype=np.uint32)
+    assert (argb != ref.tonemap(acc, frames)).mean() < 1e-5

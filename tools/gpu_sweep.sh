@@ -3,5 +3,5 @@
 mkdir -p gpurun_out
 for cfg in "$@"; do
   echo "== $cfg"
-  env $(echo $cfg | tr ';' ' ') timeout 200 python tools/render_once.py 2 32 4194304 fast 2 1 2>&1 | tail -1
+  env $(echo $cfg | tr ';' ' ') timeout 200 python tools/render_once.py 2 32 0 fast 2 1 2>&1 | tail -1
 done

@@ -303,6 +303,14 @@ LaunchDims launch_dims(const trt_ctx* c) {
     if (const char* e = getenv("TRT_SHADE_MINB")) d.shade_minb = atoi(e);
     if (const char* e = getenv("TRT_SHADE_BLOCK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512) d.shade_block = v; }
     if (const char* e = getenv("TRT_REGEN_BLOCK")) d.regen_block = std::max(32, std::min(256, atoi(e) / 32 * 32));
+    d.fused_refill = true;
+    if (const char* e = getenv("TRT_FUSED_REFILL")) d.fused_refill = atoi(e) != 0;
+    d.shadow_pair = false;
+    if (const char* e = getenv("TRT_SHADOW_PAIR")) d.shadow_pair = atoi(e) != 0;
+    d.merged_trace = true;
+    if (const char* e = getenv("TRT_MERGED_TRACE")) d.merged_trace = atoi(e) != 0;
+    d.finish_below = 128 << 10;
+    if (const char* e = getenv("TRT_FINISH_BELOW")) d.finish_below = std::max(0, atoi(e));
     d.compact_quarters = 3;
     if (const char* e = getenv("TRT_COMPACT_QUARTERS")) d.compact_quarters = std::max(1, std::min(3, atoi(e)));
     if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
@@ -471,6 +479,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         st.visit_cap = c->pool_cap;
         st.samples_left = true;
         st.mostly_live = true;
+        st.finish_below = 0;
         // Issue batches of iterations, staying one batch ahead of the completion poll.
         // near_drain: the job can reach its drain phase within the batches in flight (the poll is up to two
         // batches old; an iteration starts about capacity / 6 samples) -- from here on the batches are short.
@@ -521,6 +530,9 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
             st.visit_cap = std::min(st.visit_cap, hc.active_cap);
             if (hc.next_sample == hc.total_samples) st.samples_left = false;
             st.mostly_live = (long long)hc.alive * 2 > (long long)hc.active_cap;
+            // the poll is up to two batches old and the live paths shrink by a quarter per iteration: let the tail
+            // kernel ride along from well above its threshold (it decides on the device)
+            st.finish_below = (!st.samples_left && (long long)hc.alive <= 16ll * dims.finish_below) ? dims.finish_below : 0;
             if (near_drain) batch = kTailBatchIterations;
             b++;
             if (issued > max_iterations) {
@@ -889,6 +901,14 @@ int trt_tonemap(trt_ctx* c, const float* d_accum, int w, int h, int frames, uint
     if (int rc = use_device(c)) return rc;
     wf_tonemap(d_accum, w * h, frames, d_argb, c->stream);
     c->launches += 1;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int trt_tonemap_stream(const float* d_accum, int n_pixels, int frames, uint32_t* d_argb, void* cuda_stream) {
+    if (!d_accum || !d_argb) return fail(TRT_ERR_ARG, "null pointer");
+    if (n_pixels <= 0 || frames <= 0) return fail(TRT_ERR_ARG, "bad dimensions");
+    wf_tonemap(d_accum, n_pixels, frames, d_argb, (cudaStream_t)cuda_stream);
     CU(cudaGetLastError());
     return 0;
 }

@@ -56,6 +56,8 @@ __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity
     ctl->compact_go = 0;
     ctl->alive = capacity;   // prepare subtracts n_free and adds n_regen
     ctl->n_regen = 0;
+    ctl->regen_base = 0;
+    ctl->refill_ticket = 0;
 }
 
 __global__ void k_reset_counters(Control* ctl) {
@@ -118,10 +120,11 @@ __global__ void __launch_bounds__(kBlock) k_compact_move(PoolView pool, const Co
     const int n = ctl->compact_a;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int src = list_a[i], dst = list_b[i];
-        // `hit` and `sh_d` stay behind: compaction runs between shadow(i) and extend(i+1), so the shadow ray
-        // has been traced (dst is a dead slot, its flag is already clear; src is never visited again) and the
-        // hit record is rewritten by extend before shade reads it
+        // `hit` stays behind: it is rewritten by extend before shade reads it.  The shadow ray moves along: with
+        // the combined traversal kernel the shadow rays of the last shade pass are traced AFTER this compaction
+        // (src is never visited again, so its stale flag does no harm)
         const float4 o = pool.ray_o[src], d = pool.ray_d[src], t = pool.thr[src], r = pool.rad[src], pe = pool.pend[src];
+        const float4 sh = pool.sh_d[src];
         const uint4 ra = pool.rng_a[src];
         const uint2 rb = pool.rng_b[src];
         pool.ray_o[dst] = o;
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(kBlock) k_compact_move(PoolView pool, const Co
         pool.thr[dst] = t;
         pool.rad[dst] = r;
         pool.pend[dst] = pe;
+        pool.sh_d[dst] = sh;
         pool.rng_a[dst] = ra;
         pool.rng_b[dst] = rb;
     }
@@ -252,6 +256,205 @@ __global__ void __launch_bounds__(kBlock, 6) k_regen(PoolView pool, const int* _
         pool.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
         pool.rng_a[slot] = make_uint4(rng.v0, rng.v1, rng.v2, rng.v3);
         pool.rng_b[slot] = make_uint2(rng.v4, rng.d);
+    }
+}
+
+// ---- refill: free scan + bookkeeping + regeneration in ONE kernel ------------------------------
+// One thread per dead-mask word (32 slots), kRefillBlock words per block.  A block
+//   1. scans its mask words (the slots that ended in the last shade pass) into a slot list in shared memory,
+//   2. reserves that many camera samples with one atomicAdd on Control::next_sample (clamped to the job),
+//   3. regenerates them, kRefillBlock samples per batch: the samples of a batch are consecutive pixels of one
+//      frame, i.e. they sit in one image row (two at a row boundary), so the 4-bit-window table of M^(w*row)
+//      (12.8 KB, xorwow.cuh) is staged in shared memory as five word planes -- for a fixed window the 16 entries of
+//      a plane fall into 16 different banks, so the 200 look-ups of a sample are conflict-free LDS.32 instead
+//      of 80 scattered global loads; lanes whose row is not staged (images narrower than a batch) use the
+//      global table,
+//   4. the block that finishes last does what the single-thread k_prepare used to do: clamps next_sample,
+//      counts the samples, resets the traversal cursor and decides about a drain-phase compaction.
+// Which sample lands in which slot depends on the order the blocks reserve their ranges; the image does not
+// (a sample's RNG stream is a function of its frame and pixel alone).
+constexpr int kRefillBlock = 256;
+constexpr int kRefillSlots = kRefillBlock * 32;
+
+TRT_DEV void xw_matvec_planes(const uint32_t* __restrict__ tab, const uint32_t in[5], uint32_t out[5]) {
+    uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0;
+#pragma unroll
+    for (int w = 0; w < 5; w++) {
+        const uint32_t bits = in[w];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t e = (uint32_t)((w * 8 + k) * 16) + ((bits >> (4 * k)) & 15u);
+            r0 ^= tab[e];
+            r1 ^= tab[kXwWindowEntries + e];
+            r2 ^= tab[2 * kXwWindowEntries + e];
+            r3 ^= tab[3 * kXwWindowEntries + e];
+            r4 ^= tab[4 * kXwWindowEntries + e];
+        }
+    }
+    out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4;
+}
+
+__global__ void __launch_bounds__(kRefillBlock) k_refill(PoolView pool, Control* ctl, JobParams job, int compact_quarters,
+                                                         int samples_left) {
+    __shared__ uint32_t s_tab[2][5 * kXwWindowEntries];
+    __shared__ uint16_t s_list[kRefillSlots];
+    __shared__ int s_warp[kRefillBlock / 32];
+    __shared__ int s_take;
+    __shared__ unsigned long long s_base;
+    const int cap = ctl->active_cap;
+    const int n_words = (cap + 31) >> 5;
+    const int w0 = blockIdx.x * kRefillBlock;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (w0 < n_words) {
+        // 1. dead slots of this block -> s_list (positions relative to the block's first slot)
+        const int wi = w0 + (int)threadIdx.x;
+        uint32_t m = wi < n_words ? pool.dead_mask[wi] : 0u;
+        const int c = __popc(m);
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < kRefillBlock / 32; i++) {
+            const int v = s_warp[i];
+            if (i < (int)warp) before += v;
+            total += v;
+        }
+        // 2. reserve the samples
+        if (threadIdx.x == 0) {
+            int take = 0;
+            unsigned long long base = 0;
+            if (total > 0 && samples_left) {
+                base = atomicAdd(&ctl->next_sample, (unsigned long long)total);
+                const unsigned long long all = ctl->total_samples;
+                take = base >= all ? 0 : (int)min((unsigned long long)total, all - base);
+            }
+            if (total != take) atomicAdd(&ctl->alive, take - total);
+            s_take = take;
+            s_base = base;
+        }
+        if (samples_left) {
+            int at = before + incl - c;
+            const int rel = (int)threadIdx.x << 5;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                s_list[at++] = (uint16_t)(rel + b);
+            }
+        }
+        __syncthreads();
+        // 3. regenerate
+        const int take = s_take;
+        if (take > 0) {
+            const unsigned long long base = s_base;
+            const unsigned pixels = (unsigned)(job.rc.width * job.rc.height);
+            const int first_slot = w0 << 5;
+            int staged0 = -1, staged1 = -1;  // rows whose tables sit in s_tab[0] / s_tab[1] (block-uniform)
+            for (int q = 0; q < take; q += kRefillBlock) {
+                // frame / pixel of the batch's first sample (one 64-bit division per batch, not per sample) and the
+                // rows of its first and last sample
+                const unsigned long long sa = base + (unsigned long long)q;
+                const unsigned long long fa = sa / pixels;
+                const unsigned pa = (unsigned)(sa - fa * pixels);
+                unsigned pb = pa + (unsigned)(min(kRefillBlock, take - q) - 1);
+                while (pb >= pixels) pb -= pixels;
+                const int row_a = (int)(pa / (unsigned)job.rc.width), row_b = (int)(pb / (unsigned)job.rc.width);
+                const bool have_a = row_a == staged0 || row_a == staged1;
+                const bool have_b = row_b == staged0 || row_b == staged1;
+                if (!have_a || !have_b) {
+                    __syncthreads();  // the previous batch has finished reading the tables
+                    // row_a goes to the buffer that does not hold row_b (and vice versa)
+                    int slot_a = -1, slot_b = -1;
+                    if (!have_a) slot_a = (have_b && row_b == staged0) ? 1 : 0;
+                    if (!have_b && row_b != row_a) slot_b = !have_a ? (slot_a ^ 1) : (row_a == staged0 ? 1 : 0);
+                    for (int i = threadIdx.x; i < kXwWindowEntries; i += kRefillBlock) {
+                        if (slot_a >= 0) {
+                            const uint4 a = __ldg(job.row_a + (size_t)row_a * kXwWindowEntries + i);
+                            const uint32_t b = __ldg(job.row_b + (size_t)row_a * kXwWindowEntries + i);
+                            uint32_t* t = s_tab[slot_a];
+                            t[i] = a.x; t[kXwWindowEntries + i] = a.y; t[2 * kXwWindowEntries + i] = a.z;
+                            t[3 * kXwWindowEntries + i] = a.w; t[4 * kXwWindowEntries + i] = b;
+                        }
+                        if (slot_b >= 0) {
+                            const uint4 a = __ldg(job.row_a + (size_t)row_b * kXwWindowEntries + i);
+                            const uint32_t b = __ldg(job.row_b + (size_t)row_b * kXwWindowEntries + i);
+                            uint32_t* t = s_tab[slot_b];
+                            t[i] = a.x; t[kXwWindowEntries + i] = a.y; t[2 * kXwWindowEntries + i] = a.z;
+                            t[3 * kXwWindowEntries + i] = a.w; t[4 * kXwWindowEntries + i] = b;
+                        }
+                    }
+                    if (slot_a == 0) staged0 = row_a;
+                    if (slot_a == 1) staged1 = row_a;
+                    if (slot_b == 0) staged0 = row_b;
+                    if (slot_b == 1) staged1 = row_b;
+                    __syncthreads();
+                }
+                const int r = q + (int)threadIdx.x;
+                if (r < take) {
+                    const int slot = first_slot + (int)s_list[r];
+                    unsigned upix = pa + threadIdx.x;
+                    int f = (int)fa;
+                    while (upix >= pixels) { upix -= pixels; f++; }
+                    const int pix = (int)upix;                  // reference pixel index i
+                    const int row = pix / job.rc.width, col = pix - row * job.rc.width;
+                    const int y = job.rc.height - 1 - row;      // i = (h-1-y)*w + x  (reference :322)
+                    const XwColVec* cv = job.col_vecs + (size_t)f * job.rc.width + col;
+                    const uint4 ca = __ldg(reinterpret_cast<const uint4*>(cv));
+                    const uint2 cb = __ldg(reinterpret_cast<const uint2*>(cv) + 2);
+                    const uint32_t in[5] = {ca.x, ca.y, ca.z, ca.w, cb.x};
+                    uint32_t o[5];
+                    if (row == staged0) xw_matvec_planes(s_tab[0], in, o);
+                    else if (row == staged1) xw_matvec_planes(s_tab[1], in, o);
+                    else xw_matvec_window(job.row_a + (size_t)row * kXwWindowEntries, job.row_b + (size_t)row * kXwWindowEntries, in, o);
+                    Xorwow rng;
+                    rng.v0 = o[0]; rng.v1 = o[1]; rng.v2 = o[2]; rng.v3 = o[3]; rng.v4 = o[4];
+                    rng.d = cb.y;
+                    const Ray ray = primary_ray(job.cam, col, y, job.rc.width, job.rc.height, rng);
+                    // a fresh path has throughput 1 and no radiance: neither array is written (scattered 16-byte
+                    // stores cost a read-modify-write of the 32-byte sector); the pixel index rides in ray_o.w,
+                    // which only carries a shadow-ray length from depth 1 on, until shade moves it to thr.w
+                    pool.ray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, i2f(pix));
+                    pool.ray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
+                    pool.rng_a[slot] = make_uint4(rng.v0, rng.v1, rng.v2, rng.v3);
+                    pool.rng_b[slot] = make_uint2(rng.v4, rng.d);
+                }
+            }
+        }
+    }
+    // 4. the last block to get here closes the iteration's bookkeeping
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&ctl->refill_ticket, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long all = ctl->total_samples;
+        unsigned long long next = *(volatile unsigned long long*)&ctl->next_sample;
+        if (next > all) next = all;
+        const unsigned long long started = next - ctl->regen_base;  // regen_base: next_sample after the previous refill
+        ctl->next_sample = next;
+        ctl->regen_base = next;
+        ctl->n_regen = (int)started;
+        ctl->cnt_samples += started;
+        ctl->cnt_iterations += 1;
+        ctl->cursor_extend = 0;  // cursor_shadow is reset by the shade kernel
+        ctl->refill_ticket = 0;
+        // drain phase: no sample left to start, and the live paths have dropped to the given share of the visited slots
+        const int alive = *(volatile int*)&ctl->alive;
+        const bool go = started == 0 && next == all && cap > kCompactMinCap && (long long)alive * 4 <= (long long)cap * compact_quarters;
+        ctl->compact_go = go ? 1 : 0;
+        if (go) {
+            ctl->compact_new_cap = max(kCompactMinCap, (alive + kShadeMaxBlock - 1) / kShadeMaxBlock * kShadeMaxBlock);
+            ctl->compact_a = ctl->compact_b = 0;
+        }
     }
 }
 
@@ -513,43 +716,18 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
     }
 }
 
-template <int THREADS, bool COUNT, bool WIDE>
-__global__ void __launch_bounds__(THREADS, 1)
-k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
-              int refill_below, Phases ph) {
-    constexpr int S = FastCfg<THREADS>::SC;
-    constexpr int WARPS = THREADS / 32;
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* s_nodes = smem;
-    uint2* s_stack = reinterpret_cast<uint2*>(smem + (size_t)k_smem * kSmemNodeStride);
-    float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
-    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
-    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
-    float4* s_top = reinterpret_cast<float4*>(s_queue + WARPS * kQueueBytesClosest);  // (v0|id, e1, e2) per root-level primitive
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+// The closest-hit work of one warp: `stage` / `bars` / `queue` are the warp's own staging buffers, mbarriers and
+// tree-ray queue, `stk_base` the shared-window address of this thread's first stack entry.
+template <int THREADS, int S, bool COUNT, bool WIDE>
+TRT_DEV void extend_phase(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl, int k_smem,
+                          int refill_below, const Phases& ph, const unsigned char* s_nodes, uint32_t stk_base,
+                          float4* stage, uint64_t* bars, unsigned char* queue, const float4* s_top) {
+    const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
-        if ((i & 7) != 7)  // the eighth float4 of a node is padding
-            reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
-    if (threadIdx.x < kMaxTop) {
-        s_top[threadIdx.x * 3] = top.v0[threadIdx.x];
-        s_top[threadIdx.x * 3 + 1] = top.e1[threadIdx.x];
-        s_top[threadIdx.x * 3 + 2] = top.e2[threadIdx.x];
-    }
-    if (lane == 0) {
-        mbar_init(&s_bars[warp * 2], 1);
-        mbar_init(&s_bars[warp * 2 + 1], 1);
-    }
-    mbar_fence_init();
-    __syncthreads();
-
-    float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
-    uint64_t* bars = s_bars + warp * 2;
-    float4* q_o = reinterpret_cast<float4*>(s_queue + warp * kQueueBytesClosest);  // origin, d_min
-    float4* q_d = q_o + kQueueCap;                                                  // direction, winner so far (id | flag, -1 none)
-    int* q_s = reinterpret_cast<int*>(q_d + kQueueCap);                             // pool slot
+    float4* q_o = reinterpret_cast<float4*>(queue);  // origin, d_min
+    float4* q_d = q_o + kQueueCap;                    // direction, winner so far (id | flag, -1 none)
+    int* q_s = reinterpret_cast<int*>(q_d + kQueueCap);  // pool slot
     constexpr uint32_t E = THREADS * 8;  // bytes between consecutive stack entries of one lane
-    const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
     const uint32_t stk_ttop = stk_base + (S - 1) * E;
     uint2 spill[kSpillEntries];
     const int slot_limit = min(pool.capacity, ctl->active_cap);
@@ -653,36 +831,17 @@ k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
     }
 }
 
-template <int THREADS, bool COUNT, bool WIDE>
-__global__ void __launch_bounds__(THREADS, 1)
-k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
-              int refill_below, Phases ph) {
-    constexpr int S = FastCfg<THREADS>::SS;
-    constexpr int WARPS = THREADS / 32;
-    extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* s_nodes = smem;
-    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem + (size_t)k_smem * kSmemNodeStride);
-    float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
-    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
-    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+// The any-hit work of one warp.  E = bytes between consecutive stack entries of a lane: THREADS * 4 in the stand-alone
+// kernel (conflict free); THREADS * 8 in the combined kernel, where a thread's entries sit where its closest-hit
+// entries sit, so that a warp can move on to the closest-hit rays while other warps are still tracing shadow rays.
+template <int THREADS, int S, uint32_t E, bool COUNT, bool WIDE, bool PAIR>
+TRT_DEV void shadow_phase(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl, int k_smem,
+                          int refill_below, const Phases& ph, const unsigned char* s_nodes, uint32_t stk_base,
+                          float4* stage, uint64_t* bars, unsigned char* queue) {
+    const unsigned lane = threadIdx.x & 31u;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
-        if ((i & 7) != 7)  // the eighth float4 of a node is padding
-            reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
-    if (lane == 0) {
-        mbar_init(&s_bars[warp * 2], 1);
-        mbar_init(&s_bars[warp * 2 + 1], 1);
-    }
-    mbar_fence_init();
-    __syncthreads();
-
-    float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
-    uint64_t* bars = s_bars + warp * 2;
-    float4* q_o = reinterpret_cast<float4*>(s_queue + warp * kQueueBytesShadow);  // origin, max_dist
-    float4* q_d = q_o + kQueueCap;                                                 // direction, pool slot
-    constexpr uint32_t E = THREADS * 4;
-    const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
+    float4* q_o = reinterpret_cast<float4*>(queue);  // origin, max_dist
+    float4* q_d = q_o + kQueueCap;                    // direction, pool slot
     const uint32_t stk_ttop = stk_base + (S - 1) * E;
     uint32_t spill[kSpillEntries];
     const int slot_limit = min(pool.capacity, ctl->active_cap);
@@ -755,7 +914,8 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
 #pragma unroll 1
         for (;;) {
             if (COUNT && lane == 0) dbg_tsteps++;
-            shadow_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
+            if (PAIR) shadow_tri_step2<E, S, COUNT>(sc, st, stk_base, &wc);
+            else shadow_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
             const unsigned m = __ballot_sync(0xffffffffu, !st.occluded && st.tp != stk_ttop);
             if (__popc(m) < ph.tri_min) break;
         }
@@ -780,6 +940,283 @@ k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, 
         warp_add(&ctl->dbg[11], dbg_tsteps);
         warp_add(&ctl->dbg[12], dbg_chunks);
     }
+}
+
+// top of the tree -> shared memory (112-byte stride: the eighth float4 of a node is padding)
+template <int THREADS>
+TRT_DEV void stage_nodes(unsigned char* s_nodes, const SceneDev& sc, int k_smem) {
+    for (int i = threadIdx.x; i < k_smem * 8; i += THREADS)
+        if ((i & 7) != 7)
+            reinterpret_cast<float4*>(s_nodes)[(i >> 3) * (kSmemNodeStride / 16) + (i & 7)] = __ldg(sc.wide_nodes + i);
+}
+
+template <int THREADS, bool COUNT, bool WIDE>
+__global__ void __launch_bounds__(THREADS, 1)
+k_extend_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
+              int refill_below, Phases ph) {
+    constexpr int S = FastCfg<THREADS>::SC;
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_nodes = smem;
+    uint2* s_stack = reinterpret_cast<uint2*>(smem + (size_t)k_smem * kSmemNodeStride);
+    float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
+    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
+    float4* s_top = reinterpret_cast<float4*>(s_queue + WARPS * kQueueBytesClosest);  // (v0|id, e1, e2) per root-level primitive
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    stage_nodes<THREADS>(s_nodes, sc, k_smem);
+    if (threadIdx.x < kMaxTop) {
+        s_top[threadIdx.x * 3] = top.v0[threadIdx.x];
+        s_top[threadIdx.x * 3 + 1] = top.e1[threadIdx.x];
+        s_top[threadIdx.x * 3 + 2] = top.e2[threadIdx.x];
+    }
+    if (lane == 0) {
+        mbar_init(&s_bars[warp * 2], 1);
+        mbar_init(&s_bars[warp * 2 + 1], 1);
+    }
+    mbar_fence_init();
+    __syncthreads();
+    extend_phase<THREADS, S, COUNT, WIDE>(pool, sc, top, ctl, k_smem, refill_below, ph, s_nodes, smem_addr(s_stack + threadIdx.x),
+                                          s_stage + warp * (kStageBytesPerWarp / 16), s_bars + warp * 2,
+                                          s_queue + warp * kQueueBytesClosest, s_top);
+}
+
+template <int THREADS, bool COUNT, bool WIDE>
+__global__ void __launch_bounds__(THREADS, 1)
+k_shadow_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
+              int refill_below, Phases ph) {
+    constexpr int S = FastCfg<THREADS>::SS;
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_nodes = smem;
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(smem + (size_t)k_smem * kSmemNodeStride);
+    float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
+    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 2);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    stage_nodes<THREADS>(s_nodes, sc, k_smem);
+    if (lane == 0) {
+        mbar_init(&s_bars[warp * 2], 1);
+        mbar_init(&s_bars[warp * 2 + 1], 1);
+    }
+    mbar_fence_init();
+    __syncthreads();
+    shadow_phase<THREADS, S, THREADS * 4, COUNT, WIDE, false>(pool, sc, top, ctl, k_smem, refill_below, ph, s_nodes,
+                                                              smem_addr(s_stack + threadIdx.x),
+                                                              s_stage + warp * (kStageBytesPerWarp / 16), s_bars + warp * 2,
+                                                              s_queue + warp * kQueueBytesShadow);
+}
+
+// Shadow rays of the previous shade pass, then the closest-hit rays of this iteration, in ONE persistent launch:
+// the two ray sets are independent (both only need that shade pass and this iteration's refill), so a warp that
+// runs out of shadow chunks goes straight on to closest-hit chunks -- the tail of the any-hit work, during which
+// the stand-alone kernel leaves most of an SM idle, is filled with closest-hit work, and an iteration has one
+// launch, one start-up (tree top -> shared memory) and one tail instead of two.  No CTA barrier separates the
+// phases: staging buffers, mbarriers (a pair per phase) and queue are per warp, and a thread's any-hit stack
+// entries sit in the low words of its own closest-hit entries.
+template <int THREADS, bool COUNT, bool WIDE, bool PAIR>
+__global__ void __launch_bounds__(THREADS, 1)
+k_trace_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, Control* ctl, int k_smem,
+             int refill_below, Phases ph_closest, Phases ph_shadow) {
+    constexpr int S = FastCfg<THREADS>::SC;
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* s_nodes = smem;
+    uint2* s_stack = reinterpret_cast<uint2*>(smem + (size_t)k_smem * kSmemNodeStride);
+    float4* s_stage = reinterpret_cast<float4*>(s_stack + S * THREADS);
+    uint64_t* s_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(s_stage) + WARPS * kStageBytesPerWarp);
+    unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 4);
+    float4* s_top = reinterpret_cast<float4*>(s_queue + WARPS * kQueueBytesClosest);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (ctl->active_cap <= 0) return;  // the job's last paths were finished by k_finish_paths: nothing to visit
+    stage_nodes<THREADS>(s_nodes, sc, k_smem);
+    if (threadIdx.x < kMaxTop) {
+        s_top[threadIdx.x * 3] = top.v0[threadIdx.x];
+        s_top[threadIdx.x * 3 + 1] = top.e1[threadIdx.x];
+        s_top[threadIdx.x * 3 + 2] = top.e2[threadIdx.x];
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) mbar_init(&s_bars[warp * 4 + i], 1);
+    }
+    mbar_fence_init();
+    __syncthreads();
+    const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
+    float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
+    unsigned char* queue = s_queue + warp * kQueueBytesClosest;
+    // any-hit entries (4 bytes): lane l uses bytes [4l, 4l+4) of the 256-byte row its warp owns in every entry plane
+    // (the closest-hit entries of the warp's lanes fill the same rows, 8 bytes per lane): conflict free, and private
+    // to the warp in both phases
+    const uint32_t stk_base_sh = smem_addr(s_stack + (threadIdx.x & ~31u)) + lane * 4;
+    shadow_phase<THREADS, S, THREADS * 8, COUNT, WIDE, PAIR>(pool, sc, top, ctl, k_smem, refill_below, ph_shadow, s_nodes, stk_base_sh,
+                                                             stage, s_bars + warp * 4, queue);
+    __syncwarp();
+    extend_phase<THREADS, S, COUNT, WIDE>(pool, sc, top, ctl, k_smem, refill_below, ph_closest, s_nodes, stk_base, stage,
+                                          s_bars + warp * 4 + 2, queue, s_top);
+}
+
+// ---- drain tail: the last paths of a job run to completion in ONE launch ------------------------
+// Near the end of a job the wavefront iterations carry a few ten thousand paths each, and each of them still
+// costs three launches with their start-up and tail (the last 25 iterations of a 64-spp C2 job: 2.7 ms for
+// under 1 % of the work).  Once the live paths have dropped to `finish_below` and no sample is left, this
+// kernel takes every remaining path through extend -> shade -> shadow in a loop, one path per thread, with
+// the same device functions the wavefront kernels use (same top phase, same wide-BVH steps, same winner
+// verification, same shade_vertex, same order of the radiance additions), so the image is the one the
+// remaining iterations would have produced.  The decision is made on the device from Control (every thread reads
+// the same values); k_finish_commit then empties the pool bound, which turns the iterations still queued behind
+// it into no-ops, and the host's next poll sees alive == 0.
+constexpr int kFinishBlock = 128;
+constexpr int kFinishStack = 16;
+
+TRT_DEV bool finish_wanted(const Control* ctl, int finish_below) {
+    return ctl->active_cap > 0 && ctl->alive <= finish_below && ctl->next_sample >= ctl->total_samples;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kFinishBlock) k_finish_paths(PoolView pool, Control* ctl, SceneDev sc,
+                                                               const __grid_constant__ TopPrims top, JobParams job,
+                                                               int finish_below) {
+    __shared__ uint2 s_stack[kFinishStack * kFinishBlock];
+    if (!finish_wanted(ctl, finish_below)) return;
+    constexpr uint32_t E = kFinishBlock * 8;
+    constexpr int S = kFinishStack;
+    const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
+    const uint32_t stk_ttop = stk_base + (S - 1) * E;
+    const int cap = ctl->active_cap;
+    unsigned n_closest = 0, n_shadow = 0, n_replays = 0;
+    WideCounts wc = {0, 0};
+    // any-hit query for the lanes with `want`; called by all lanes of the warp
+    auto occluded_by = [&](const F3 o, const F3 d, float max_dist, bool want) -> bool {
+        __syncwarp();
+        const int verdict = top_shadow(top, o, d, max_dist, want);
+        if (want) n_shadow++;
+        bool occ = want && verdict == 1;
+        if (want && verdict == 2) {
+            uint32_t spill[kSpillEntries];
+            ShadowRay st;
+            shadow_begin(st, make_float4(o.x, o.y, o.z, max_dist), make_float4(d.x, d.y, d.z, 0.f), stk_base, stk_ttop, E);
+            while (!shadow_done<E, S>(st, stk_base)) {
+                shadow_node_step<E, S, COUNT, false>(nullptr, 0, sc, st, stk_base, spill, &wc);
+                shadow_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
+            }
+            occ = st.occluded;
+        }
+        __syncwarp();
+        return occ;
+    };
+    for (int first = blockIdx.x * kFinishBlock; first < cap; first += gridDim.x * kFinishBlock) {
+        const int slot = first + (int)threadIdx.x;  // cap is a multiple of the block size
+        const float4 d4 = pool.ray_d[slot];
+        const int flags = f2i(d4.w);
+        const int state = flags & 0xff;
+        bool active = state == SLOT_ACTIVE;
+        const bool live = state != SLOT_DEAD;
+        PathVertexIO io;
+        io.shadow = false;
+        io.shadow_ray.o = io.shadow_ray.d = io.shadow_contrib = f3(0.f, 0.f, 0.f);
+        io.shadow_max_dist = 0.f;
+        io.depth = (flags >> 8) & 0xff;
+        io.prev_mode = (flags >> 16) & 0xff;
+        int pix = 0;
+        io.thr = f3(1.f, 1.f, 1.f);
+        io.rad = f3(0.f, 0.f, 0.f);
+        io.ray.o = io.ray.d = f3(0.f, 0.f, 0.f);
+        io.rng.v0 = io.rng.v1 = io.rng.v2 = io.rng.v3 = io.rng.v4 = io.rng.d = 0;
+        F3 pend = f3(0.f, 0.f, 0.f);
+        bool sh = false;
+        F3 sh_dir = f3(0.f, 0.f, 0.f);
+        float sh_len = 0.f;
+        if (live) {
+            const float4 o4 = pool.ray_o[slot];
+            const bool fresh = io.depth == 0;  // regenerate leaves thr / rad unwritten and the pixel in ray_o.w
+            io.ray.o = f3(o4.x, o4.y, o4.z);
+            io.ray.d = f3(d4.x, d4.y, d4.z);
+            if (fresh) {
+                pix = f2i(o4.w);
+            } else {
+                const float4 thr4 = pool.thr[slot], rad4 = pool.rad[slot], pend4 = pool.pend[slot], sh4 = pool.sh_d[slot];
+                pix = f2i(thr4.w);
+                io.thr = f3(thr4.x, thr4.y, thr4.z);
+                io.rad = f3(rad4.x, rad4.y, rad4.z);
+                pend = f3(pend4.x, pend4.y, pend4.z);
+                sh = f2i(sh4.w) == 1;
+                sh_dir = f3(sh4.x, sh4.y, sh4.z);
+                sh_len = o4.w;
+            }
+            const uint4 ra = pool.rng_a[slot];
+            const uint2 rb = pool.rng_b[slot];
+            io.rng.v0 = ra.x; io.rng.v1 = ra.y; io.rng.v2 = ra.z; io.rng.v3 = ra.w;
+            io.rng.v4 = rb.x; io.rng.d = rb.y;
+        }
+        // the shadow ray the last shade pass left behind, then what the next shade pass would do first
+        if (occluded_by(io.ray.o, sh_dir, sh_len, sh)) pend = f3(0.f, 0.f, 0.f);
+        if (live && io.depth > 0) io.rad = v_add(io.rad, pend);
+        bool ended = live && !active;  // SLOT_FINISH
+        while (__any_sync(0xffffffffu, active)) {
+            float t_hit = 0.f;
+            int id = -1;
+            if (active) {  // closest hit: top phase, tree phase, winner verification
+                n_closest++;
+                const TopResult tr = top_closest(top, io.ray.o, io.ray.d);
+                t_hit = tr.d_min;
+                id = tr.id;
+                if (tr.enters) {
+                    uint2 spill[kSpillEntries];
+                    ClosestRay st;
+                    closest_begin(st, make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, 0.f),
+                                  make_float4(io.ray.d.x, io.ray.d.y, io.ray.d.z, 0.f), tr.d_min, tr.id, stk_base, stk_ttop);
+                    while (!closest_done<E, S>(st, stk_base)) {
+                        closest_node_step<E, S, COUNT, false>(nullptr, 0, sc, st, stk_base, spill, &wc);
+                        closest_tri_step2<E, S, COUNT>(sc, st, stk_base, &wc);
+                    }
+                    t_hit = st.d_min;
+                    id = st.id;
+                }
+                if (resolve_hit(sc, io.ray.o, io.ray.d, t_hit, id)) n_replays++;
+            }
+            bool want_shadow = false;
+            if (active) {
+                if (id < 0 || !shade_vertex(sc, job.rc, io, id, t_hit)) {
+                    active = false;  // miss, light source, Russian roulette ...
+                    ended = true;
+                } else {
+                    io.depth++;
+                    want_shadow = io.shadow;
+                }
+            }
+            // next-event estimate of this vertex (the wavefront folds it in at the start of the next shade pass)
+            const bool occ = occluded_by(io.ray.o, io.shadow_ray.d, io.shadow_max_dist, want_shadow);
+            if (want_shadow && !occ) io.rad = v_add(io.rad, io.shadow_contrib);
+            if (active && io.depth >= job.rc.max_depth) {  // the reference loop ends after max_depth vertices
+                active = false;
+                ended = true;
+            }
+        }
+        if (ended) {
+            F3 rad = io.rad;
+            if (filter_sample(rad)) {  // reference :739-759
+                float* a = job.accum + (size_t)pix * 4;
+                atomicAdd(a + 0, rad.x);
+                atomicAdd(a + 1, rad.y);
+                atomicAdd(a + 2, rad.z);
+            }
+        }
+    }
+    __syncwarp();
+    warp_add(&ctl->cnt_closest, n_closest);
+    warp_add(&ctl->cnt_shadow, n_shadow);
+    warp_add(&ctl->cnt_replays, n_replays);
+    if (COUNT) {
+        warp_add(&ctl->cnt_nodes, wc.nodes);
+        warp_add(&ctl->cnt_tris, wc.tris);
+    }
+}
+
+__global__ void k_finish_commit(Control* ctl, int finish_below) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || !finish_wanted(ctl, finish_below)) return;
+    ctl->alive = 0;
+    ctl->active_cap = 0;
+    ctl->compact_go = 0;
 }
 
 // ---- parity / test entry points -------------------------------------------------------------
@@ -925,6 +1362,40 @@ size_t fast_smem_bytes(int k_smem, bool shadow) {
            (size_t)(THREADS / 32) * (kStageBytesPerWarp + 16 + (shadow ? kQueueBytesShadow : kQueueBytesClosest));
 }
 
+template <int THREADS>
+size_t trace_smem_bytes(int k_smem) {  // the combined kernel: closest-hit layout with two more mbarriers per warp
+    return fast_smem_bytes<THREADS>(k_smem, false) + (size_t)(THREADS / 32) * 16;
+}
+
+template <int THREADS, bool COUNT>
+void launch_trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
+                       const LaunchDims& dims, cudaStream_t s) {
+    if (dims.wide_loads && THREADS == 768) {
+        k_trace_fast<768, COUNT, true, false><<<dims.sms, 768, trace_smem_bytes<768>(0), s>>>(
+            pool, sc, top, ctl, 0, dims.refill_below, dims.closest_phases, dims.shadow_phases);
+        return;
+    }
+    // the two extra mbarriers per warp come out of the staged nodes
+    const int extra_nodes = (int)(((size_t)(THREADS / 32) * 16 + kSmemNodeStride - 1) / kSmemNodeStride);
+    const int k = max(0, min(dims.smem_nodes - extra_nodes, sc.n_wide_nodes));
+    if (THREADS == 768 && dims.shadow_pair) {
+        k_trace_fast<768, COUNT, false, true><<<dims.sms, 768, trace_smem_bytes<768>(k), s>>>(
+            pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, dims.shadow_phases);
+        return;
+    }
+    k_trace_fast<THREADS, COUNT, false, false><<<dims.sms, THREADS, trace_smem_bytes<THREADS>(k), s>>>(
+        pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, dims.shadow_phases);
+}
+template <bool COUNT>
+void trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl, const LaunchDims& dims,
+                cudaStream_t s) {
+    switch (dims.fast_threads) {
+    case 1024: launch_trace_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
+    case 768: launch_trace_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
+    default: launch_trace_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
+    }
+}
+
 template <int THREADS, bool COUNT>
 void launch_extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                         const LaunchDims& dims, cudaStream_t s) {
@@ -995,6 +1466,16 @@ int wf_configure() {
     rc |= opt_in_smem(k_extend_fast<768, true, true>);
     rc |= opt_in_smem(k_shadow_fast<768, false, true>);
     rc |= opt_in_smem(k_shadow_fast<768, true, true>);
+    rc |= opt_in_smem(k_trace_fast<512, false, false, false>);
+    rc |= opt_in_smem(k_trace_fast<512, true, false, false>);
+    rc |= opt_in_smem(k_trace_fast<768, false, false, false>);
+    rc |= opt_in_smem(k_trace_fast<768, true, false, false>);
+    rc |= opt_in_smem(k_trace_fast<768, false, false, true>);
+    rc |= opt_in_smem(k_trace_fast<768, true, false, true>);
+    rc |= opt_in_smem(k_trace_fast<1024, false, false, false>);
+    rc |= opt_in_smem(k_trace_fast<1024, true, false, false>);
+    rc |= opt_in_smem(k_trace_fast<768, false, true, false>);
+    rc |= opt_in_smem(k_trace_fast<768, true, true, false>);
     return rc;
 }
 
@@ -1049,7 +1530,7 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
                           int* compact_lists) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
-    const bool overlap = st.overlap && st.samples_left;
+    const bool overlap = st.overlap && st.samples_left && !dims.fused_refill;
     cudaStream_t s = st.main, side = overlap ? st.side : st.main;
     int launched = 0;
     // marks[0..5]; st.mark_mask selects which of them are recorded
@@ -1057,19 +1538,26 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
     if (overlap) cudaStreamWaitEvent(side, st.fork, 0);
     mark(0, side);
     const int visit = min(pool.capacity, st.visit_cap);
-    // slots that ended in the last shade pass -> free list + count (the count also feeds `alive` in the drain phase)
-    k_free_scan<<<((visit + 31) / 32 + kScanBlock - 1) / kScanBlock, kScanBlock, 0, side>>>(pool.dead_mask, free_list, ctl);
-    k_prepare<<<1, 32, 0, side>>>(ctl, dims.compact_quarters);
-    launched += 2;
-    if (st.samples_left) {
-        // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
-        // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up;
-        // small CTAs so that one fits beside the persistent shadow CTA of an SM
-        const int kRegenBlock = dims.regen_block;
-        const int regen_full = (pool.capacity + kRegenBlock - 1) / kRegenBlock;
-        const int regen_blocks = min(regen_full, max(2 * persistent, regen_full / 4));
-        k_regen<<<regen_blocks, kRegenBlock, 0, side>>>(pool, free_list, ctl, job);
-        launched++;
+    if (dims.fused_refill) {
+        // free scan + bookkeeping + regeneration of the slots that ended in the last shade pass, one kernel
+        k_refill<<<((visit + 31) / 32 + kRefillBlock - 1) / kRefillBlock, kRefillBlock, 0, s>>>(
+            pool, ctl, job, dims.compact_quarters, st.samples_left ? 1 : 0);
+        launched += 1;
+    } else {
+        // slots that ended in the last shade pass -> free list + count (the count also feeds `alive` in the drain phase)
+        k_free_scan<<<((visit + 31) / 32 + kScanBlock - 1) / kScanBlock, kScanBlock, 0, side>>>(pool.dead_mask, free_list, ctl);
+        k_prepare<<<1, 32, 0, side>>>(ctl, dims.compact_quarters);
+        launched += 2;
+        if (st.samples_left) {
+            // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
+            // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up;
+            // small CTAs so that one fits beside the persistent shadow CTA of an SM
+            const int kRegenBlock = dims.regen_block;
+            const int regen_full = (pool.capacity + kRegenBlock - 1) / kRegenBlock;
+            const int regen_blocks = min(regen_full, max(2 * persistent, regen_full / 4));
+            k_regen<<<regen_blocks, kRegenBlock, 0, side>>>(pool, free_list, ctl, job);
+            launched++;
+        }
     }
     mark(1, side);
     if (overlap) {
@@ -1085,7 +1573,10 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
         launched += 3;
     }
     mark(2, s);
-    if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
+    const bool merged = MODE == TRT_TRAVERSE_FAST && dims.merged_trace && dims.fused_refill;
+    // merged: the shadow rays of the previous shade pass and this iteration's closest-hit rays in one launch
+    if (merged) trace_fast<COUNT>(pool, sc, top, ctl, dims, s);
+    else if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
     mark(3, s);
     // blocks beyond active_cap return at once, but 16 Ki of them still cost 0.1 ms: size the grid by the bound
@@ -1103,11 +1594,20 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
         k_shade<COUNT, F, kShadeMaxBlock, 2><<<shade_blocks, dims.shade_block, 0, s>>>(pool, ctl, sc, job, eager);
     }
     mark(4, s);
-    if (st.overlap) cudaEventRecord(st.fork, s);  // the next side part may start now
-    if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);
-    else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
+    if (st.overlap && !dims.fused_refill) cudaEventRecord(st.fork, s);  // the next side part may start now
+    if (!merged) {
+        if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);
+        else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
+    }
     mark(5, s);
-    return launched + 3;
+    if (merged && st.finish_below > 0) {
+        // drain tail: once few enough paths are left they are run to completion in one launch (decided on the device)
+        const int blocks = max(1, min((visit + kFinishBlock - 1) / kFinishBlock, dims.sms * 16));
+        k_finish_paths<COUNT><<<blocks, kFinishBlock, 0, s>>>(pool, ctl, sc, top, job, st.finish_below);
+        k_finish_commit<<<1, 32, 0, s>>>(ctl, st.finish_below);
+        launched += 2;
+    }
+    return launched + (merged ? 2 : 3);
 }
 
 int wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,

@@ -50,6 +50,7 @@ struct Control {
     // drain-phase compaction (wavefront.cu k_compact_*): slots [0, active_cap) are the only ones any
     // kernel visits; it shrinks when the job has no samples left and the live paths have halved
     int active_cap, compact_go, compact_new_cap, compact_a, compact_b;
+    int refill_ticket;  // blocks of the running k_refill that have finished (the last one closes the iteration's bookkeeping)
     // counters (see trt_counters)
     unsigned long long cnt_samples, cnt_closest, cnt_shadow, cnt_replays, cnt_iterations;
     unsigned long long cnt_nodes, cnt_tris;                // all queries (COUNT builds only)
@@ -94,6 +95,10 @@ struct LaunchDims {
     int shade_minb;     // 128-thread shade CTAs: resident CTAs per SM the register allocation aims for (8, 10, 12, 14)
     int regen_block;    // threads per regenerate CTA (it shares SMs with the persistent shadow CTAs)
     int compact_quarters;  // drain phase: compact when live paths <= this many quarters of the visited slots (1..3)
+    int finish_below;      // drain tail: paths alive at which k_finish_paths runs the rest of the job to completion (0 = never)
+    bool shadow_pair;      // combined kernel: any-hit triangle steps test two triangles of a leaf at once
+    bool merged_trace;     // shadow rays of the previous shade pass + closest-hit rays in one persistent launch (needs fused_refill)
+    bool fused_refill;     // free scan + bookkeeping + regeneration in one kernel on the main stream (k_refill)
     Phases closest_phases, shadow_phases;
 };
 
@@ -121,6 +126,7 @@ struct IterStreams {
     // and next_sample only grows within a job)
     int visit_cap = 0x7fffffff;  // upper bound of Control::active_cap: sizes the shade grid
     bool samples_left = true;    // false: the job has handed out its last sample, nothing to regenerate
+    int finish_below = 0;        // > 0: the drain-tail kernel rides along and takes over once this few paths are alive
     bool mostly_live = true;     // at least half of the visited slots hold a path: shade requests a slot's whole state up front
 };
 // one wavefront iteration on the streams of `st`; returns the number of kernels it launched
