@@ -512,7 +512,7 @@ def main():
                trt.default_opts(pool_paths=args.pool, count_rays=1), frame_stride=world)
     cc = ctx.counters()
     info = ctx.scene_info()
-    extend_s = kt["extend_ms"] * 1e-3 / args.steps           # closest-hit traversal time per step, timed region
+    extend_s = kt["extend_ms"] * 1e-3 / args.steps           # traversal kernel time per step, timed region
     launches_per_step = kt["iterations"] / args.steps if args.steps else 0
     hbm_peak, hbm_src = measured_hbm()
     mp = machine_peaks(local) if world == 1 else None
@@ -524,10 +524,25 @@ def main():
     #   FP32: 48 flop per 4-wide node step (24 sub + 24 mul), 51 per triangle test (tree + root-level list)
     #   L2  : node records (128 B) + triangle records (48 B) fetched (served by shared memory / L1 / L2)
     #   HBM : the ray read (32 B) and the hit write (8 B) of every query
-    top_tris = cc["closest_rays"] * info["n_top_prims"]
-    flop_step = cc["nodes_closest"] * 48.0 + (cc["tris_closest"] + top_tris) * 51.0
-    scene_bytes_step = cc["nodes_closest"] * info["wide_node_bytes"] + cc["tris_closest"] * info["tri_record_bytes"]
-    stream_bytes_step = cc["closest_rays"] * 40.0
+    # The dominant kernel is the combined traversal kernel k_trace_fast: the any-hit (shadow) rays of the previous shade
+    # pass and the closest-hit rays of the iteration in one persistent launch, so the terms count both ray kinds.
+    # Root-level list: a closest-hit ray runs the full triangle test for every primitive (51 flop); a shadow ray
+    # runs the two thin-axis products first (4 flop per primitive) and the full tests only when a lane passes.
+    merged = os.environ.get("TRT_MERGED_TRACE", "1") != "0" and os.environ.get("TRT_FUSED_REFILL", "1") != "0"
+    if merged:
+        k_nodes, k_tris = cc["nodes_fetched"], cc["tris_tested"]
+        top_flop = cc["closest_rays"] * info["n_top_prims"] * 51.0 + cc["shadow_rays"] * info["n_top_prims"] * 4.0
+        stream_bytes_step = cc["closest_rays"] * 40.0 + cc["shadow_rays"] * 32.0
+        k_rays = cc["closest_rays"] + cc["shadow_rays"]
+        kname, kkey = "k_trace_fast (any-hit + closest-hit traversal, one persistent launch per iteration)", "k_trace_fast"
+    else:
+        k_nodes, k_tris = cc["nodes_closest"], cc["tris_closest"]
+        top_flop = cc["closest_rays"] * info["n_top_prims"] * 51.0
+        stream_bytes_step = cc["closest_rays"] * 40.0
+        k_rays = cc["closest_rays"]
+        kname, kkey = "k_extend_fast (closest-hit traversal)", "k_extend_fast"
+    flop_step = k_nodes * 48.0 + k_tris * 51.0 + top_flop
+    scene_bytes_step = k_nodes * info["wide_node_bytes"] + k_tris * info["tri_record_bytes"]
     t_fp32 = flop_step / fp32_peak
     t_l2 = scene_bytes_step / l2_peak if l2_peak else None
     t_hbm = stream_bytes_step / (hbm_peak * 1e9)
@@ -537,7 +552,7 @@ def main():
     bound = max(terms, key=terms.get)
     # DRAM traffic of one full-pool launch (ncu) against the duration of the full-pool launches of this run
     tr = committed_traffic() or {}
-    traffic = tr.get("k_extend_fast_dram_bytes_per_launch")
+    traffic = tr.get(kkey + "_dram_bytes_per_launch")
     full = sorted(r[1] for r in per_iter)[-max(1, len(per_iter) // 3):] if per_iter else []
     full_launch_ms = full[len(full) // 2] if full else None  # median of the longest third = the full-pool launches
     if bound == "fp32":
@@ -547,7 +562,7 @@ def main():
     else:
         achieved, peak, unit = stream_bytes_step / extend_s / 1e9, hbm_peak, "GB/s"
     roofline = {
-        "kernel": "k_extend_fast (closest-hit traversal)", "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+        "kernel": kname, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
         "frac": achieved / peak, "traffic": traffic,
         "recompute": "frac = t_bound / t_kernel with t_bound = max over `terms_s_per_step`; t_kernel = kernel_s_per_step",
         "kernel_s_per_step": extend_s, "launches_per_step": launches_per_step,
@@ -555,15 +570,15 @@ def main():
         "term_inputs": {"flop_per_step": flop_step, "fp32_peak_tflops": fp32_peak / 1e12, "fp32_peak_source": fp32_src,
                         "node_tri_bytes_per_step": scene_bytes_step, "l2_read_peak_gbs": l2_peak / 1e9 if l2_peak else None,
                         "ray_hit_stream_bytes_per_step": stream_bytes_step, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src},
-        "per_ray": {"nodes": cc["nodes_closest"] / max(cc["closest_rays"], 1),
-                    "tris": cc["tris_closest"] / max(cc["closest_rays"], 1),
+        "per_ray": {"rays_per_step": k_rays, "nodes": k_nodes / max(k_rays, 1),
+                    "tris": k_tris / max(k_rays, 1),
                     "root_level_tris": info["n_top_prims"], "node_bytes": info["wide_node_bytes"],
                     "tri_bytes": info["tri_record_bytes"], "flop_per_node_step": 48, "flop_per_triangle_test": 51},
         "dram": {"bytes_per_full_pool_launch_ncu": traffic, "full_pool_launch_ms": full_launch_ms,
                  "frac_of_hbm_peak": (traffic / (full_launch_ms * 1e-3) / 1e9 / hbm_peak) if (traffic and full_launch_ms) else None,
-                 "l2_bytes_per_full_pool_launch_ncu": tr.get("k_extend_fast_l2_bytes_per_launch"),
-                 "l2_gbs": (tr["k_extend_fast_l2_bytes_per_launch"] / (full_launch_ms * 1e-3) / 1e9)
-                 if (tr.get("k_extend_fast_l2_bytes_per_launch") and full_launch_ms) else None},
+                 "l2_bytes_per_full_pool_launch_ncu": tr.get(kkey + "_l2_bytes_per_launch"),
+                 "l2_gbs": (tr[kkey + "_l2_bytes_per_launch"] / (full_launch_ms * 1e-3) / 1e9)
+                 if (tr.get(kkey + "_l2_bytes_per_launch") and full_launch_ms) else None},
         "machine_peaks": mp,
         "note": "nothing on this path is a dense contraction (no tensor-core term).  `bound` is the largest of the three "
                 "SURVEY 8(d) terms: the node/triangle records the traversal consumes against the L2 read bandwidth measured on "
@@ -573,7 +588,7 @@ def main():
                 "issue-slot utilisation at ~23 of 32 lanes per instruction, most issued instructions being compares, selects "
                 "and stack traffic rather than the algorithmic flops (FP32 term: `terms_s_per_step.fp32 / kernel_s_per_step`).",
         "kernel_share_of_step": {k: split[k] / max(split_ms, 1e-9) for k in ("regen_ms", "extend_ms", "shade_ms", "shadow_ms")},
-        "kernel_share_note": "one extra step with events at every kernel boundary; regenerate runs beside the shadow kernel, so the shares add up to more than 1"}
+        "kernel_share_note": "one extra step with events at every kernel boundary; with the combined traversal kernel `extend_ms` is that kernel (any-hit + closest-hit) and `shadow_ms` is empty; `regen_ms` is k_refill (free scan + bookkeeping + regeneration)"}
 
     # rank 0 at N=1 only: under torchrun the host cores are shared (and OMP_NUM_THREADS is forced to 1)
     cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(scene, cam, w, h)

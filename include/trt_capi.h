@@ -68,6 +68,9 @@ typedef struct {
     uint64_t tris_closest;      /* triangle tests by closest-hit queries only */
     uint64_t tree_closest;      /* closest-hit queries that entered the tree (count_rays builds, FAST mode) */
     uint64_t tree_shadow;       /* any-hit queries that entered the tree */
+    uint64_t check_violations;  /* TRT_DEBUG_CHECKS=1 renders: slot-state invariants found broken by the kernels that write
+                                   slots they do not own by construction (refill: the slot must be dead and hold no shadow
+                                   ray; compaction: source live, destination dead).  Must stay 0. */
 } trt_counters;
 
 /* Device time of the last trt_render per kernel family, from CUDA events recorded on the
@@ -127,6 +130,19 @@ int trt_upload_scene_ex(trt_ctx* ctx, const void* objects, int n_objects,
                         const void* nodes, int n_nodes,
                         const int* lights, int n_lights,
                         const trt_image* textures, int n_textures, int builder);
+/* Instanced upload: a scene made of `extra` objects followed by n_instances placements of ONE mesh.  The reference
+ * has no instancing: a field of meshes is n calls of load_obj on the same file (src/loader.cpp:22-103, a full parse
+ * each) appending to one vector, and init_scene_data uploads that vector.  Here the mesh is parsed once (unit:
+ * n_unit records of 112 bytes, e.g. trt_load_obj with offset 0 / scale 1), `instances` holds n_instances records of
+ * 4 floats (offset.xyz, scale), and the object array -- extra[0..n_extra), then for instance i the unit triangles
+ * with every vertex at fma(v, scale_i, offset_i), exactly the loader's arithmetic (:51) -- is written by a kernel
+ * on the device and never exists on the host.  The BVH is built on the device (as trt_upload_scene_ex with
+ * TRT_BUILD_DEVICE_LBVH and nodes == NULL); lights index the final array. */
+int trt_upload_instanced(trt_ctx* ctx, const void* extra, int n_extra, const void* unit, int n_unit,
+                         const float* instances, int n_instances, const int* lights, int n_lights,
+                         const trt_image* textures, int n_textures);
+/* The uploaded object array back on the host (tests: the instanced scene equals the loader's, byte for byte). */
+int trt_get_objects(trt_ctx* ctx, void* out, int cap);
 int trt_scene_info_get(trt_ctx* ctx, trt_scene_info* out);
 
 /* Render = n_frames calls of launch_render_kernel (include/renderer.h:57,

@@ -161,3 +161,36 @@ def test_c5_field_incoherent_rays_device_tree_equals_reference_order(trt, scenes
         assert float((a[0] >= 0).float().mean()) > 0.3 and hit_mesh > 0.05
     finally:
         c.close()
+
+
+def c5_parts(trt, assets, grid):
+    """The C5 field as (extra objects, unit mesh, placements): what create_config_scene(5) instances on the host."""
+    objs, _ = trt.create_scene(5, assets, grid=grid)
+    unit = trt.load_obj(str(assets / "teapot.obj"))  # offset 0, scale 1: the file's own vertices
+    extra = objs[:2]                                  # floor + light
+    inst = np.array([(-175.0 + 9.0 * ix, 0.0, 60.0 - 9.0 * iz, 1.2) for iz in range(grid) for ix in range(grid)],
+                    dtype=np.float32)
+    return objs, extra, unit, inst
+
+
+def test_instanced_upload_builds_the_loaders_object_array_on_the_device(trt, assets, ctx):
+    """f3: the mesh is parsed once and placed by a kernel; the object array the device ends up with is,
+    byte for byte, the one the loader builds by re-reading the file per instance (reference
+    src/loader.cpp:22-103, one load_obj call per placement), and renders to the same first-hit ids."""
+    grid = 3
+    objs, extra, unit, inst = c5_parts(trt, assets, grid)
+    lights = trt.collect_lights(objs)
+    ctx.upload_instanced(extra, unit, inst, lights)
+    got = ctx.get_objects()
+    assert got.tobytes() == np.ascontiguousarray(objs).tobytes()
+    # the reference loader itself, per placement (offset, scale as load_obj arguments)
+    one = trt.load_obj(str(assets / "teapot.obj"), offset=tuple(float(v) for v in inst[4][:3]), scale=float(inst[4][3]))
+    n = len(unit)
+    assert got[2 + 4 * n: 2 + 5 * n].tobytes() == np.ascontiguousarray(one).tobytes()
+    cam, w, h = trt.config_camera(5, 480, 270)
+    ids_a = dev_zeros(w * h, torch.int32)
+    ctx.trace_primary(w, h, 1, cam, trt.TRAVERSE_FAST, d_id=ids_a)
+    ctx.init_scene_data(objs, [], None, lights, builder=trt.BUILD_DEVICE_LBVH)
+    ids_b = dev_zeros(w * h, torch.int32)
+    ctx.trace_primary(w, h, 1, cam, trt.TRAVERSE_FAST, d_id=ids_b)
+    assert torch.equal(ids_a, ids_b) and int((ids_a >= 2).sum()) > 1000  # teapots are visible

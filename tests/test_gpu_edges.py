@@ -130,3 +130,20 @@ def test_render_longer_than_one_job(trt, ref, ctx, assets):
     sc = trt.HostScene.from_config(1, assets)
     cam, w, h = trt.config_camera(1, 96, 64)
     radiance_gate(trt, ref, ctx, sc, cam, w, h, 600, "C1 96x64, 600 frames")
+
+
+@pytest.mark.parametrize("config,w,h,spp,pool", [(1, 640, 480, 16, 0), (2, 960, 540, 8, 0), (2, 640, 360, 12, 40448)])
+def test_slot_state_invariants_hold_under_debug_checks(trt, ref, ctx, assets, monkeypatch, config, w, h, spp, pool):
+    """Race / ownership evidence without compute-sanitizer: with TRT_DEBUG_CHECKS=1 the kernels that overwrite slots
+    they do not own by construction verify the slot state first -- refill: the slot ended in the last shade pass (dead,
+    no shadow ray waiting); drain compaction: source live and beyond the new bound, destination dead and inside it.
+    The counter must stay 0, the checked render must pass the same gates as the plain one, and the job must have
+    gone through compactions and the drain-tail kernel (iterations well below the plain wavefront's)."""
+    monkeypatch.setenv("TRT_DEBUG_CHECKS", "1")
+    sc = trt.HostScene.from_config(config, assets)
+    cam, _, _ = trt.config_camera(config, w, h)
+    ctx.reset_counters()
+    radiance_gate(trt, ref, ctx, sc, cam, w, h, spp, f"debug checks C{config} pool {pool}", pool_paths=pool)
+    c = ctx.counters()
+    assert c["samples"] == w * h * spp
+    assert c["check_violations"] == 0

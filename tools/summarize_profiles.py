@@ -35,8 +35,9 @@ if rep.exists():
     idx = {h: i for i, h in enumerate(rows[0])}
     units = rows[1]
     tr = []
+    kkey = "k_trace_fast" if any("k_trace_fast" in d[idx["Kernel Name"]] for d in rows[2:]) else "k_extend_fast"
     for d in rows[2:]:
-        if "k_extend_fast" in d[idx["Kernel Name"]]:
+        if kkey in d[idx["Kernel Name"]]:
             def b(name):
                 v = float(d[idx[name]].replace(",", ""))
                 u = units[idx[name]]
@@ -46,9 +47,9 @@ if rep.exists():
     if tr:
         n = len(tr)
         (out / "traffic.json").write_text(json.dumps({
-            "k_extend_fast_dram_bytes_per_launch": sum(t[0] for t in tr) / n,
-            "k_extend_fast_l2_bytes_per_launch": sum(t[1] for t in tr) / n,
-            "k_extend_fast_ms_under_ncu": sum(t[2] for t in tr) / n,
+            kkey + "_dram_bytes_per_launch": sum(t[0] for t in tr) / n,
+            kkey + "_l2_bytes_per_launch": sum(t[1] for t in tr) / n,
+            kkey + "_ms_under_ncu": sum(t[2] for t in tr) / n,
             "launches_sampled": n, "what": "full-pool (32 Mi slots) launches of one 64-spp C2 step, ncu --set full",
             "source": f"profiles/{tag}_ncu_full_summary.txt"}))
         print("traffic", tr)

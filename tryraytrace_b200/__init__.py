@@ -46,7 +46,8 @@ class Opts(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("samples", "closest_rays", "shadow_rays", "nodes_fetched",
                                           "tris_tested", "replays", "iterations", "kernel_launches",
-                                          "nodes_closest", "tris_closest", "tree_closest", "tree_shadow")]
+                                          "nodes_closest", "tris_closest", "tree_closest", "tree_shadow",
+                                          "check_violations")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -294,6 +295,28 @@ class Context:
         arr = (Image * max(len(imgs), 1))(*imgs)
         _check(lib().trt_upload_scene_ex(self._h, _np_ptr(objs), len(objs), _np_ptr(nd) if len(nd) else None, len(nd),
                                          _np_ptr(li) if len(li) else None, len(li), arr, len(imgs), int(builder)))
+
+    def upload_instanced(self, extra, unit, instances, light_indices, texture_files=()):
+        """extra: OBJECT records placed first; unit: the mesh, parsed once; instances: (n, 4) float32 rows of
+        (offset.xyz, scale).  The object array is generated and the BVH built on the device (trt_upload_instanced)."""
+        ex = np.ascontiguousarray(extra, dtype=OBJECT)
+        un = np.ascontiguousarray(unit, dtype=OBJECT)
+        inst = np.ascontiguousarray(instances, dtype=np.float32).reshape(-1, 4)
+        li = np.ascontiguousarray(light_indices, dtype=np.int32)
+        imgs, keep = [], []
+        for f in texture_files:
+            a = np.ascontiguousarray(load_ppm(f))
+            keep.append(a)
+            imgs.append(Image(a.shape[1], a.shape[0], a.ctypes.data))
+        arr = (Image * max(len(imgs), 1))(*imgs)
+        _check(lib().trt_upload_instanced(self._h, _np_ptr(ex) if len(ex) else None, len(ex), _np_ptr(un), len(un),
+                                          _np_ptr(inst), len(inst), _np_ptr(li) if len(li) else None, len(li), arr, len(imgs)))
+
+    def get_objects(self):
+        n = self.scene_info()["n_objects"]
+        out = np.zeros(n, dtype=OBJECT)
+        _check(lib().trt_get_objects(self._h, _np_ptr(out), n))
+        return out
 
     def upload(self, scene: HostScene, builder=0):
         self.init_scene_data(scene.objects, scene.texture_files, scene.nodes, scene.lights, builder)

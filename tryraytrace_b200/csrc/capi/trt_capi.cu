@@ -58,8 +58,6 @@ struct trt_ctx {
     int sms = 148;
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // created by trt_create
-    cudaStream_t side_stream = nullptr; // overlapped regeneration (kernels/wavefront.cuh IterStreams)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_poll[2] = {nullptr, nullptr};
     float last_ms = 0.f;
     unsigned long long launches = 0;
@@ -70,6 +68,7 @@ struct trt_ctx {
     float4* d_ref_nodes = nullptr;
     int* d_lights = nullptr;
     float4* d_wide_nodes = nullptr;
+    uint4* d_cnodes = nullptr;  // compressed 64-byte form of the wide nodes (big scenes; then d_wide_nodes is released)
     float4* d_tris = nullptr;
     bool wide_from_pool = false;  // d_wide_nodes / d_tris came from the stream-ordered pool (device builder)
     std::vector<cudaArray_t> tex_arrays;
@@ -90,7 +89,6 @@ struct trt_ctx {
     int pool_cap = 0;
     void* pool_mem = nullptr;
     PoolView pool{};
-    int* d_free = nullptr;
     int* d_compact = nullptr;  // drain-phase compaction lists (kernels/wavefront.cu k_compact_*)
     // scratch pool of the parity entry points (FAST mode runs the production kernels over it)
     int scratch_cap = 0;
@@ -140,6 +138,8 @@ void free_scene(trt_ctx* c) {
         cudaFree(c->d_tris);
     }
     c->wide_from_pool = false;
+    cudaFree(c->d_cnodes);
+    c->d_cnodes = nullptr;
     c->d_objects = c->d_ref_nodes = c->d_wide_nodes = c->d_tris = nullptr;
     c->d_lights = nullptr;
     c->have_scene = false;
@@ -223,25 +223,21 @@ int ensure_col_vecs(trt_ctx* c, size_t entries) {
     return 0;
 }
 
-// One allocation, carved into the SoA arrays of PoolView (+ the free list when asked for).
-int alloc_pool(int cap, bool with_free_list, void** mem, PoolView* pool, int** free_list) {
+// One allocation, carved into the arrays of PoolView (+ the dead mask of the render pool).
+int alloc_pool(int cap, bool render_pool, void** mem, PoolView* pool) {
     const size_t n = (size_t)cap;
-    // 7 float4/uint4 arrays + hit (float2) + rng_b (uint2) + free list (int) + dead mask (1 bit per slot)
-    const size_t bytes = n * (7 * 16 + 2 * 8 + (with_free_list ? 4 : 0)) + (with_free_list ? n / 8 + 64 : 0);
+    // od (32) + rs (32) + thr, pend, sh_d (16 each) + hit (8) = 120 bytes per slot + dead mask (1 bit per slot)
+    const size_t bytes = n * (2 * 32 + 3 * 16 + 8) + (render_pool ? n / 8 + 64 : 0);
     CU(cudaMalloc(mem, bytes));
     char* p = (char*)*mem;
     auto take = [&](size_t b) { void* r = p; p += b; return r; };
-    pool->ray_o = (float4*)take(n * 16);
-    pool->ray_d = (float4*)take(n * 16);
+    pool->od = (float4*)take(n * 32);
+    pool->rs = (uint4*)take(n * 32);
     pool->thr = (float4*)take(n * 16);
-    pool->rad = (float4*)take(n * 16);
     pool->pend = (float4*)take(n * 16);
     pool->sh_d = (float4*)take(n * 16);
-    pool->rng_a = (uint4*)take(n * 16);
     pool->hit = (float2*)take(n * 8);
-    pool->rng_b = (uint2*)take(n * 8);
-    if (free_list) *free_list = with_free_list ? (int*)take(n * 4) : nullptr;
-    pool->dead_mask = with_free_list ? (uint32_t*)take(n / 8 + 64) : nullptr;
+    pool->dead_mask = render_pool ? (uint32_t*)take(n / 8 + 64) : nullptr;
     pool->capacity = cap;
     return 0;
 }
@@ -254,7 +250,7 @@ int ensure_pool(trt_ctx* c, int cap) {
     c->pool_mem = nullptr;
     c->d_compact = nullptr;
     c->pool_cap = 0;
-    if (int rc = alloc_pool(cap, true, &c->pool_mem, &c->pool, &c->d_free)) return rc;
+    if (int rc = alloc_pool(cap, true, &c->pool_mem, &c->pool)) return rc;
     // two lists of up to cap entries each (live slots beyond the new bound / dead slots below it; the bound is
     // clamped to kCompactMinCap, so with a small pool the dead list can hold nearly the whole pool)
     CU(cudaMalloc(&c->d_compact, 2 * ((size_t)cap + 512) * sizeof(int)));
@@ -271,7 +267,7 @@ int ensure_scratch(trt_ctx* c, int n) {
     cudaFree(c->scratch_mem);
     c->scratch_mem = nullptr;
     c->scratch_cap = 0;
-    if (int rc = alloc_pool(cap, false, &c->scratch_mem, &c->scratch, nullptr)) return rc;
+    if (int rc = alloc_pool(cap, false, &c->scratch_mem, &c->scratch)) return rc;
     c->scratch_cap = cap;
     return 0;
 }
@@ -292,25 +288,20 @@ LaunchDims launch_dims(const trt_ctx* c) {
     const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
     d.smem_nodes = fit;
     if (const char* e = getenv("TRT_SMEM_NODES")) d.smem_nodes = std::max(0, std::min(fit, atoi(e)));
-    // trees beyond a few MB (B200 sweep: +3 % at 37 MB, +14 % at 356 MB, -3 % at 0.2 MB): the node fetch is
-    // bound by L1 requests, use the 256-bit load path
-    d.wide_loads = (size_t)c->sc.n_wide_nodes * sizeof(WideNode) > ((size_t)16 << 20);
-    if (const char* e = getenv("TRT_WIDE_LOADS")) d.wide_loads = atoi(e) != 0;
+    // trees beyond a few MB: the node fetch is bound by L1 requests; the upload has compressed the nodes to 64 bytes
+    // (two 256-bit loads per node step) and the kernels read that form, nothing staged
+    d.wide_loads = c->sc.cnodes != nullptr;
     d.refill_below = 32;
-    d.regen_block = 128;
     d.shade_block = 128;
     d.shade_minb = 8;
     if (const char* e = getenv("TRT_SHADE_MINB")) d.shade_minb = atoi(e);
     if (const char* e = getenv("TRT_SHADE_BLOCK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512) d.shade_block = v; }
-    if (const char* e = getenv("TRT_REGEN_BLOCK")) d.regen_block = std::max(32, std::min(256, atoi(e) / 32 * 32));
-    d.fused_refill = true;
-    if (const char* e = getenv("TRT_FUSED_REFILL")) d.fused_refill = atoi(e) != 0;
-    d.shadow_pair = false;
-    if (const char* e = getenv("TRT_SHADOW_PAIR")) d.shadow_pair = atoi(e) != 0;
     d.merged_trace = true;
     if (const char* e = getenv("TRT_MERGED_TRACE")) d.merged_trace = atoi(e) != 0;
     d.finish_below = 128 << 10;
     if (const char* e = getenv("TRT_FINISH_BELOW")) d.finish_below = std::max(0, atoi(e));
+    d.debug_checks = false;
+    if (const char* e = getenv("TRT_DEBUG_CHECKS")) d.debug_checks = atoi(e) != 0;
     d.compact_quarters = 3;
     if (const char* e = getenv("TRT_COMPACT_QUARTERS")) d.compact_quarters = std::max(1, std::min(3, atoi(e)));
     if (const char* e = getenv("TRT_REFILL")) d.refill_below = std::max(1, std::min(32, atoi(e)));
@@ -457,10 +448,10 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;
 
     c->marks_used = 0;
-    IterStreams st{c->stream, c->side_stream, c->ev_fork, c->ev_join, true};
+    IterStreams st;
+    st.main = c->stream;
     st.mark_mask = o.time_kernels == 2 ? 0x0c : 0x3f;  // 2: only the marks around the extend kernel
     c->marks_mask = st.mark_mask;
-    if (const char* e = getenv("TRT_OVERLAP")) st.overlap = atoi(e) != 0;
     bool compact = true;
     if (const char* e = getenv("TRT_COMPACT")) compact = atoi(e) != 0;
     const LaunchDims dims = launch_dims(c);
@@ -472,10 +463,9 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         fill_job(c, job, d_accum, w, h, first + f0 * stride, nf, stride, cam, o);
         wf_col_table(c->d_col_pows, c->n_col_bits, w, job.first_frame_seed, stride, o.seed_base, nf, c->d_col_vecs,
                      c->stream);
-        wf_init_pool(c->pool, c->d_free, c->d_ctl, c->stream);
+        wf_init_pool(c->pool, c->stream);
         wf_begin_job(c->d_ctl, pixels * nf, c->pool_cap, c->stream);
         c->launches += 3;
-        if (st.overlap) CU(cudaEventRecord(st.fork, c->stream));
         st.visit_cap = c->pool_cap;
         st.samples_left = true;
         st.mostly_live = true;
@@ -499,7 +489,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
                     marks = c->marks.data() + c->marks_used;
                     c->marks_used += 6;
                 }
-                c->launches += (unsigned long long)wf_iteration(c->pool, c->d_free, c->d_ctl, c->sc, c->top, job, o.traversal,
+                c->launches += (unsigned long long)wf_iteration(c->pool, c->d_ctl, c->sc, c->top, job, o.traversal,
                                                                 o.count_rays != 0, dims, st, marks,
                                                                 compact_near && compact ? c->d_compact : nullptr);
             }
@@ -547,6 +537,8 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     return 0;
 }
 
+int upload_core(trt_ctx* c, const Object* objs, float4* d_objs_ready, int n_objects, const LinearBVHNode* nd, int n_nodes,
+                bool have_ref, const int* lights, int n_lights, const trt_image* textures, int n_textures, int builder);
 }  // namespace
 
 extern "C" {
@@ -577,9 +569,6 @@ int init_ctx(trt_ctx* c, int device) {
         return fail(TRT_ERR_CUDA, "cannot opt in to %d bytes of shared memory per block", smem_optin);
     }
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->stream = c->own_stream;
     CU(cudaEventCreate(&c->ev_begin));
     CU(cudaEventCreate(&c->ev_end));
@@ -627,9 +616,8 @@ int trt_destroy(trt_ctx* c) {
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     cudaFree(c->d_accum_own);
     for (cudaEvent_t e : c->marks) cudaEventDestroy(e);
-    for (cudaEvent_t e : {c->ev_begin, c->ev_end, c->ev_poll[0], c->ev_poll[1], c->ev_fork, c->ev_join})
+    for (cudaEvent_t e : {c->ev_begin, c->ev_end, c->ev_poll[0], c->ev_poll[1]})
         if (e) cudaEventDestroy(e);
-    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     cudaGetLastError();
     delete c;
@@ -672,11 +660,25 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
         }
     }
     if (int rc = use_device(c)) return rc;
+    return upload_core(c, objs, nullptr, n_objects, nd, n_nodes, have_ref, lights, n_lights, textures, n_textures, builder);
+}
+
+}  // extern "C"
+
+namespace {
+// Everything behind the argument checks.  `objs` is the host object array, or nullptr when `d_objs_ready` already
+// holds the objects on the device (trt_upload_instanced: ownership passes to the context; device builder only).
+int upload_core(trt_ctx* c, const Object* objs, float4* d_objs_ready, int n_objects, const LinearBVHNode* nd, int n_nodes,
+                bool have_ref, const int* lights, int n_lights, const trt_image* textures, int n_textures, int builder) {
     CU(cudaStreamSynchronize(c->stream));
     free_scene(c);
 
-    CU(cudaMalloc(&c->d_objects, (size_t)n_objects * sizeof(Object)));
-    CU(cudaMemcpy(c->d_objects, objs, (size_t)n_objects * sizeof(Object), cudaMemcpyHostToDevice));
+    if (d_objs_ready) {
+        c->d_objects = d_objs_ready;
+    } else {
+        CU(cudaMalloc(&c->d_objects, (size_t)n_objects * sizeof(Object)));
+        CU(cudaMemcpy(c->d_objects, objs, (size_t)n_objects * sizeof(Object), cudaMemcpyHostToDevice));
+    }
     if (have_ref) {
         CU(cudaMalloc(&c->d_ref_nodes, (size_t)n_nodes * sizeof(LinearBVHNode)));
         CU(cudaMemcpy(c->d_ref_nodes, nd, (size_t)n_nodes * sizeof(LinearBVHNode), cudaMemcpyHostToDevice));
@@ -739,6 +741,29 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
         n_wide = (int)wb.nodes.size(); n_tris = (int)wb.tris.size(); n_top = wb.n_top_prims; depth = wb.depth;
         n_underivable = wb.n_underivable;
     }
+    // Compressed nodes for trees far larger than the caches (north-star subsystem 1; kernels/traverse_fast.cuh CNode):
+    // conservative 8-bit child boxes, 64 bytes per node.  TRT_COMPRESSED=1/0 forces / forbids it (tests, tuning).
+    bool compress = (size_t)n_wide * sizeof(WideNode) > ((size_t)16 << 20);
+    if (const char* e = getenv("TRT_COMPRESSED")) compress = atoi(e) != 0;
+    if (compress && n_wide > 0) {
+        int* d_bad = nullptr;
+        int bad = 0;
+        CU(cudaMalloc(&c->d_cnodes, (size_t)n_wide * 64));
+        CU(cudaMalloc(&d_bad, sizeof(int)));
+        CU(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+        wf_compress_nodes(c->d_wide_nodes, n_wide, c->d_cnodes, d_bad, c->stream);
+        CU(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d_bad);
+        if (bad) {  // a box the grid cannot contain (not seen so far): keep the uncompressed nodes
+            cudaFree(c->d_cnodes);
+            c->d_cnodes = nullptr;
+        } else {    // the kernels read only the compressed form from here on
+            if (c->wide_from_pool) cudaFreeAsync(c->d_wide_nodes, c->stream);
+            else cudaFree(c->d_wide_nodes);
+            c->d_wide_nodes = nullptr;
+        }
+    }
     finalize_top(tp);
     if (3 * depth + 1 > kWideStackEntries) {
         free_scene(c);
@@ -756,6 +781,7 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
     sc.n_textures = n_textures;
     for (int i = 0; i < n_textures; i++) sc.tex[i] = c->tex_objs[i];
     sc.wide_nodes = c->d_wide_nodes;
+    sc.cnodes = c->d_cnodes;
     sc.tris = c->d_tris;
     sc.n_wide_nodes = n_wide;
     sc.n_tris = n_tris;
@@ -769,7 +795,7 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
     in.n_wide_nodes = n_wide;
     in.n_wide_leaf_tris = n_tris;
     in.n_top_prims = n_top;
-    in.wide_node_bytes = (int)sizeof(WideNode);
+    in.wide_node_bytes = c->d_cnodes ? 64 : (int)sizeof(WideNode);
     in.tri_record_bytes = (int)sizeof(TriRecord);
     in.wide_depth = depth;
     in.builder = builder;
@@ -777,6 +803,61 @@ int trt_upload_scene_ex(trt_ctx* c, const void* objects, int n_objects, const vo
     in.n_underivable = n_underivable;
     c->have_scene = true;
     return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int trt_upload_instanced(trt_ctx* c, const void* extra, int n_extra, const void* unit, int n_unit,
+                         const float* instances, int n_instances, const int* lights, int n_lights,
+                         const trt_image* textures, int n_textures) {
+    if (!c) return fail(TRT_ERR_ARG, "null context");
+    if (n_extra < 0 || n_unit <= 0 || n_instances <= 0 || !unit || !instances || (n_extra > 0 && !extra))
+        return fail(TRT_ERR_ARG, "empty mesh / instance list");
+    const long long total = (long long)n_extra + (long long)n_unit * n_instances;
+    if (total >= (1ll << 29)) return fail(TRT_ERR_ARG, "too many objects");
+    if (n_lights < 0 || (n_lights > 0 && !lights)) return fail(TRT_ERR_ARG, "bad light list");
+    if (n_textures < 0 || n_textures > 5) return fail(TRT_ERR_ARG, "at most 5 textures (MAX_TEXTURES)");
+    for (int i = 0; i < n_lights; i++)
+        if (lights[i] < 0 || lights[i] >= total) return fail(TRT_ERR_ARG, "light index %d out of range", lights[i]);
+    const Object* ex = (const Object*)extra;
+    const Object* un = (const Object*)unit;
+    for (int i = 0; i < n_extra; i++)
+        if (ex[i].tex_id >= n_textures) return fail(TRT_ERR_ARG, "object %d uses texture %d, only %d given", i, ex[i].tex_id, n_textures);
+    for (int i = 0; i < n_unit; i++)
+        if (un[i].tex_id >= n_textures) return fail(TRT_ERR_ARG, "mesh triangle %d uses texture %d, only %d given", i, un[i].tex_id, n_textures);
+    if (int rc = use_device(c)) return rc;
+    // the mesh once, the placements, and a kernel that writes the 112-byte records where the reference's loader
+    // would have put them (v' = fma(v, scale, offset), src/loader.cpp:51 as compiled with contraction)
+    float4 *d_objs = nullptr, *d_unit = nullptr, *d_inst = nullptr;
+    auto cleanup = [&] { cudaFree(d_unit); cudaFree(d_inst); };
+    CU(cudaMalloc(&d_objs, (size_t)total * sizeof(Object)));
+    if (cudaMalloc(&d_unit, (size_t)n_unit * sizeof(Object)) != cudaSuccess || cudaMalloc(&d_inst, (size_t)n_instances * 16) != cudaSuccess) {
+        cleanup();
+        cudaFree(d_objs);
+        return fail(TRT_ERR_CUDA, "out of device memory for the instanced scene");
+    }
+    cudaMemcpyAsync(d_unit, unit, (size_t)n_unit * sizeof(Object), cudaMemcpyHostToDevice, c->stream);
+    cudaMemcpyAsync(d_inst, instances, (size_t)n_instances * 16, cudaMemcpyHostToDevice, c->stream);
+    if (n_extra) cudaMemcpyAsync(d_objs, extra, (size_t)n_extra * sizeof(Object), cudaMemcpyHostToDevice, c->stream);
+    wf_instance_objects(d_unit, n_unit, d_inst, n_instances, d_objs + (size_t)n_extra * 7, c->stream);
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (e != cudaSuccess) {
+        cudaFree(d_objs);
+        return fail(TRT_ERR_CUDA, "instancing kernel: %s", cudaGetErrorString(e));
+    }
+    return upload_core(c, nullptr, d_objs, (int)total, nullptr, 0, false, lights, n_lights, textures, n_textures,
+                       TRT_BUILD_DEVICE_LBVH);
+}
+
+int trt_get_objects(trt_ctx* c, void* out, int cap) {
+    if (!c || !out) return fail(TRT_ERR_ARG, "null pointer");
+    if (!c->have_scene) return fail(TRT_ERR_STATE, "no scene uploaded");
+    if (cap < c->sc.n_objects) return fail(TRT_ERR_ARG, "buffer too small: %d objects", c->sc.n_objects);
+    if (int rc = use_device(c)) return rc;
+    CU(cudaMemcpy(out, c->d_objects, (size_t)c->sc.n_objects * sizeof(Object), cudaMemcpyDeviceToHost));
+    return c->sc.n_objects;
 }
 
 int trt_upload_scene(trt_ctx* c, const void* objects, int n_objects, const void* nodes, int n_nodes,
@@ -940,6 +1021,7 @@ int trt_get_counters(trt_ctx* c, trt_counters* out) {
     out->tris_closest = hc.cnt_tris_closest;
     out->tree_closest = hc.cnt_tree_closest;
     out->tree_shadow = hc.cnt_tree_shadow;
+    out->check_violations = hc.cnt_violations;
     if (getenv("TRT_TRAV_STATS")) {  // lane-utilisation statistics of the traversal kernels (count_rays renders)
         const unsigned long long nodes_shadow = hc.cnt_nodes - hc.cnt_nodes_closest, tris_shadow = hc.cnt_tris - hc.cnt_tris_closest;
         auto line = [&](const char* name, const unsigned long long* d, unsigned long long rays, unsigned long long tree,
@@ -990,7 +1072,7 @@ int trt_kernel_times_get(trt_ctx* c, trt_kernel_times* out) {
         } else {
             CU(cudaEventElapsedTime(&ms[1], c->marks[i + 2], c->marks[i + 3]));
         }
-        t.regen_ms += ms[0];  // overlaps the previous iteration's shadow kernel unless TRT_OVERLAP=0
+        t.regen_ms += ms[0];  // k_refill
         t.extend_ms += ms[1];
         t.shade_ms += ms[2];
         t.shadow_ms += ms[3];

@@ -72,7 +72,8 @@ struct SceneDev {
     int n_objects, n_ref_nodes, n_lights, n_textures;
     cudaTextureObject_t tex[5];
     // re-laid-out arrays for the fast path
-    const float4* wide_nodes;  // 8 float4 per 4-wide node (128 B)
+    const float4* wide_nodes;  // 8 float4 per 4-wide node (128 B); nullptr when only the compressed form is kept
+    const uint4* cnodes;       // compressed form of the same nodes, 4 uint4 each (64 B, traverse_fast.cuh CNode), or nullptr
     const float4* tris;        // 3 float4 per triangle in wide-leaf order: (v0, id | flags) (v1, -) (v2, -)
     int n_wide_nodes, n_tris;
 };

@@ -355,42 +355,75 @@ struct NodeData {
 // different nodes spread over the banks), the rest sit in global memory 128 bytes apart.  Both
 // are read through ONE generic-address code path: a warp whose lanes are split between the two
 // spaces issues the seven loads once, not twice.
-// 256-bit read-only global load (sm_100: LDG.E.256): two adjacent float4 in one request
-TRT_DEV void ldg256(const unsigned char* p, float4& a, float4& b) {
-    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p));
+// Compressed node, 64 bytes (north-star subsystem 1, "compressed wide BVH"; after Ylitie, Karras & Laine 2017): the
+// child boxes of a node are stored as 8-bit grid coordinates relative to the node's own box,
+//     plane = fma(float(2^23 + q), scale_axis, base_axis),      q in [0, 255], scale a power of two,
+// i.e. the byte is dropped into the mantissa of 2^23 (one PRMT) and one FMA decodes it; base = lo - 2^23 * scale.
+// The converter (k_compress_nodes below) evaluates exactly this expression and moves q outward until the decoded
+// lo plane is <= and the decoded hi plane is >= the plane of the 128-byte node, so a compressed box CONTAINS the
+// uncompressed one: the superset argument at the top of this file is untouched, the ray only meets a few more
+// candidates.  Layout, as four 16-byte words:
+//     w0 = base.x base.y base.z scale.x | w1 = scale.y scale.z qlo_x qhi_x | w2 = qlo_y qhi_y qlo_z qhi_z | w3 = child[4]
+// (q words: child k in byte k).  Two 256-bit loads per node step instead of seven 128-bit ones, and half the
+// bytes: for trees far larger than the caches the traversal is bound by L1 requests (C5: 94-96 % of the L1TEX
+// request rate with the 128-byte node), not by arithmetic.
+// An unused child slot keeps the reference kWideEmptyRef and is made to miss explicitly (its far plane on x
+// becomes -inf * sign): an inverted box cannot be relied on here, the grid has no infinity.
+struct CNode {
+    float base[3];
+    float scale[3];
+    uint32_t qx_lo, qx_hi, qy_lo, qy_hi, qz_lo, qz_hi;
+    int child[4];
+};
+static_assert(sizeof(CNode) == 64, "CNode layout");
+
+TRT_DEV float cnode_plane(uint32_t q_word, int k, float scale, float base) {
+    // byte k of q_word into the low byte of 0x4B000000 (= 2^23 as a float): the float 2^23 + q
+    const uint32_t bits = __byte_perm(q_word, 0x4B000000u, 0x7440u + (uint32_t)k);
+    return p_fma(__uint_as_float(bits), scale, base);
 }
-TRT_DEV float4 sel4(bool take_b, const float4 a, const float4 b) {
-    return make_float4(take_b ? b.x : a.x, take_b ? b.y : a.y, take_b ? b.z : a.z, take_b ? b.w : a.w);
+TRT_DEV float4 cnode_planes(uint32_t q_word, float scale, float base) {
+    return make_float4(cnode_plane(q_word, 0, scale, base), cnode_plane(q_word, 1, scale, base),
+                       cnode_plane(q_word, 2, scale, base), cnode_plane(q_word, 3, scale, base));
+}
+TRT_DEV void ldg256u(const unsigned char* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
 }
 
 // WIDE = false: the generic path above (scenes whose tree top fits the staged / cached part).
-// WIDE = true: for trees far larger than the caches the traversal is bound by the number of L1
-// requests, seven scattered 16-byte loads per lane per node step; here the lo/hi plane vectors of
-// an axis (adjacent in the node) come in ONE 256-bit load and the near/far choice is made on the
-// registers -- four requests per node step instead of seven, nothing staged in shared memory.
+// WIDE = true: the compressed 64-byte node, nothing staged in shared memory.  The near / far choice is made on the
+// packed grid words (one select per axis), then the eight planes of an axis are decoded.
 template <bool WIDE>
-TRT_DEV void load_node(NodeData& n, const unsigned char* s_nodes, int k_smem, const float4* g_nodes, int node, int nxo,
+TRT_DEV void load_node(NodeData& n, const unsigned char* s_nodes, int k_smem, const SceneDev& sc, int node, int nxo,
                        int nyo, int nzo) {
     if (WIDE) {
-        const unsigned char* b = reinterpret_cast<const unsigned char*>(g_nodes) + (size_t)node * 128;
-        float4 lo, hi;
-        ldg256(b, lo, hi);
-        n.nx = sel4(nxo != 0, lo, hi);
-        n.fx = sel4(nxo != 0, hi, lo);
-        ldg256(b + 32, lo, hi);
-        n.ny = sel4(nyo != 32, lo, hi);
-        n.fy = sel4(nyo != 32, hi, lo);
-        ldg256(b + 64, lo, hi);
-        n.nz = sel4(nzo != 64, lo, hi);
-        n.fz = sel4(nzo != 64, hi, lo);
-        n.ch = __ldg(reinterpret_cast<const int4*>(b + 96));
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(sc.cnodes) + (size_t)node * 64;
+        uint4 w0, w1, w2, w3;
+        ldg256u(b, w0, w1);
+        ldg256u(b + 32, w2, w3);
+        const float bx = __uint_as_float(w0.x), by = __uint_as_float(w0.y), bz = __uint_as_float(w0.z);
+        const float sx = __uint_as_float(w0.w), sy = __uint_as_float(w1.x), sz = __uint_as_float(w1.y);
+        const bool negx = nxo != 0, negy = nyo != 32, negz = nzo != 64;  // the ray travels towards -axis: near = hi
+        n.nx = cnode_planes(negx ? w1.w : w1.z, sx, bx);
+        n.fx = cnode_planes(negx ? w1.z : w1.w, sx, bx);
+        n.ny = cnode_planes(negy ? w2.y : w2.x, sy, by);
+        n.fy = cnode_planes(negy ? w2.x : w2.y, sy, by);
+        n.nz = cnode_planes(negz ? w2.w : w2.z, sz, bz);
+        n.fz = cnode_planes(negz ? w2.z : w2.w, sz, bz);
+        n.ch = make_int4((int)w3.x, (int)w3.y, (int)w3.z, (int)w3.w);
+        // unused slots: far plane = -inf * sign(inv.x), so (far - o) * inv = -inf whatever the ray
+        const float kill = negx ? __int_as_float(0x7f800000) : __int_as_float(0xff800000);
+        n.fx.x = n.ch.x == kWideEmptyRef ? kill : n.fx.x;
+        n.fx.y = n.ch.y == kWideEmptyRef ? kill : n.fx.y;
+        n.fx.z = n.ch.z == kWideEmptyRef ? kill : n.fx.z;
+        n.fx.w = n.ch.w == kWideEmptyRef ? kill : n.fx.w;
         return;
     }
     const bool staged = node < k_smem;
     const unsigned char* b = staged ? s_nodes + (size_t)node * kSmemNodeStride
-                                    : reinterpret_cast<const unsigned char*>(g_nodes) + (size_t)node * 128;
+                                    : reinterpret_cast<const unsigned char*>(sc.wide_nodes) + (size_t)node * 128;
     n.nx = *reinterpret_cast<const float4*>(b + nxo);
     n.fx = *reinterpret_cast<const float4*>(b + (nxo ^ 16));
     n.ny = *reinterpret_cast<const float4*>(b + nyo);
@@ -644,7 +677,7 @@ TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const S
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node<WIDE>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    load_node<WIDE>(n, s_nodes, k_smem, sc, node, s.nxo, s.nyo, s.nzo);
     // slab intervals of the four children, packed two per instruction
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
@@ -833,7 +866,7 @@ TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const Sc
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node<WIDE>(n, s_nodes, k_smem, sc.wide_nodes, node, s.nxo, s.nyo, s.nzo);
+    load_node<WIDE>(n, s_nodes, k_smem, sc, node, s.nxo, s.nyo, s.nzo);
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
     const float4 az = plane_t(n.nz, s.o.z, s.inv.z), bz = plane_t(n.fz, s.o.z, s.inv.z);

@@ -21,40 +21,38 @@ constexpr int kCompactMinCap = 32 * 1024;  // the pool is not compacted below th
 
 TRT_DEV int pack_flags(int state, int depth, int mode) { return state | (depth << 8) | (mode << 16); }
 
-// ---- prepare: single thread, advances the queue bookkeeping between iterations --------
-__global__ void k_prepare(Control* ctl, int compact_quarters) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int n_free = ctl->n_free;
-    const unsigned long long remaining = ctl->total_samples - ctl->next_sample;
-    const int n_regen = remaining < (unsigned long long)n_free ? (int)remaining : n_free;
-    ctl->regen_base = ctl->next_sample;
-    ctl->n_regen = n_regen;
-    ctl->next_sample += (unsigned long long)n_regen;
-    ctl->alive += n_regen - n_free;
-    ctl->cnt_samples += (unsigned long long)n_regen;
-    ctl->cnt_iterations += 1;
-    ctl->n_free = 0;
-    ctl->cursor_extend = 0;  // cursor_shadow is reset by the shade kernel: with overlapped regeneration the
-                             // previous iteration's shadow kernel may still be pulling chunks
-    // drain phase: no sample left to start, and at most half of the visited slots still hold a path
-    const int cap = ctl->active_cap;
-    // (n_regen == 0: the slots this iteration's regenerate is about to fill are still marked dead)
-    const bool go = n_regen == 0 && ctl->next_sample == ctl->total_samples && cap > kCompactMinCap && (long long)ctl->alive * 4 <= (long long)cap * compact_quarters;
-    ctl->compact_go = go ? 1 : 0;
-    if (go) {
-        ctl->compact_new_cap = max(kCompactMinCap, (ctl->alive + kShadeMaxBlock - 1) / kShadeMaxBlock * kShadeMaxBlock);
-        ctl->compact_a = ctl->compact_b = 0;
-    }
+// A paired 32-byte record (PoolView::od, ::rs) in ONE 256-bit access (sm_100 LDG.E.256 / STG.E.256): a warp's 32
+// records are 1 KB contiguous, so the access is fully coalesced; two 128-bit accesses at a 32-byte stride would each
+// use half of every sector they touch.
+TRT_DEV void ld_rec(const float4* rec, float4& a, float4& b) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(rec));
+}
+TRT_DEV void ld_rec(const uint4* rec, uint4& a, uint4& b) {
+    asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(rec));
+}
+TRT_DEV void st_rec(float4* rec, const float4 a, const float4 b) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rec), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+                 : "memory");
+}
+TRT_DEV void st_rec(uint4* rec, const uint4 a, const uint4 b) {
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rec), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
 }
 
 __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->next_sample = 0;
     ctl->total_samples = total;
-    ctl->n_free = 0;         // every slot is marked ended in the dead mask (k_init_pool); the first free scan lists them all
+    ctl->n_free = 0;         // every slot is marked ended in the dead mask (k_init_pool): the first refill fills them all
     ctl->active_cap = capacity;
     ctl->compact_go = 0;
-    ctl->alive = capacity;   // prepare subtracts n_free and adds n_regen
+    ctl->alive = capacity;   // refill subtracts the slots that ended and adds the samples it starts
     ctl->n_regen = 0;
     ctl->regen_base = 0;
     ctl->refill_ticket = 0;
@@ -67,6 +65,7 @@ __global__ void k_reset_counters(Control* ctl) {
     ctl->cnt_nodes_closest = ctl->cnt_tris_closest = 0;
     ctl->cnt_tree_closest = ctl->cnt_tree_shadow = 0;
     for (int i = 0; i < 16; i++) ctl->dbg[i] = 0;
+    ctl->cnt_violations = 0;
 }
 
 __global__ void k_reset_cursors(Control* ctl) {
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(1024) k_compact_scan(PoolView pool, Control* c
         if (threadIdx.x < 2) count[threadIdx.x] = 0;
         __syncthreads();
         const int slot = first + threadIdx.x;
-        const bool live = slot < cap && (f2i(pool.ray_d[slot].w) & 0xff) != SLOT_DEAD;
+        const bool live = slot < cap && (f2i(pool.od[2 * slot + 1].w) & 0xff) != SLOT_DEAD;
         const bool to_a = live && slot >= new_cap, to_b = !live && slot < new_cap;
         const unsigned ma = __ballot_sync(0xffffffffu, to_a), mb = __ballot_sync(0xffffffffu, to_b);
         int ba = 0, bb = 0;
@@ -114,27 +113,29 @@ __global__ void __launch_bounds__(1024) k_compact_scan(PoolView pool, Control* c
 }
 
 // move: slot A[i] -> slot B[i], every array of the pool
-__global__ void __launch_bounds__(kBlock) k_compact_move(PoolView pool, const Control* __restrict__ ctl,
-                                                         const int* __restrict__ list_a, const int* __restrict__ list_b) {
+__global__ void __launch_bounds__(kBlock) k_compact_move(PoolView pool, Control* __restrict__ ctl,
+                                                         const int* __restrict__ list_a, const int* __restrict__ list_b, int debug) {
     if (!ctl->compact_go) return;
     const int n = ctl->compact_a;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int src = list_a[i], dst = list_b[i];
-        // `hit` stays behind: it is rewritten by extend before shade reads it.  The shadow ray moves along: with
-        // the combined traversal kernel the shadow rays of the last shade pass are traced AFTER this compaction
-        // (src is never visited again, so its stale flag does no harm)
-        const float4 o = pool.ray_o[src], d = pool.ray_d[src], t = pool.thr[src], r = pool.rad[src], pe = pool.pend[src];
-        const float4 sh = pool.sh_d[src];
-        const uint4 ra = pool.rng_a[src];
-        const uint2 rb = pool.rng_b[src];
-        pool.ray_o[dst] = o;
-        pool.ray_d[dst] = d;
+        if (debug) {  // the move owns neither slot by construction: source must hold a path, destination must be dead and inside the new bound
+            const bool ok = (f2i(pool.od[2 * src + 1].w) & 0xff) != SLOT_DEAD && (f2i(pool.od[2 * dst + 1].w) & 0xff) == SLOT_DEAD &&
+                            !(pool.od[2 * dst].w > 0.f) && dst < ctl->compact_new_cap && src >= ctl->compact_new_cap && src < ctl->active_cap;
+            if (!ok) atomicAdd(&ctl->cnt_violations, 1ull);
+        }
+        // `hit` stays behind: it is rewritten by the traversal before shade reads it.  The shadow ray moves along:
+        // the shadow rays of the last shade pass are traced AFTER this compaction (src is never visited again)
+        float4 o, d;
+        uint4 ra, rb;
+        ld_rec(pool.od + 2 * (size_t)src, o, d);
+        ld_rec(pool.rs + 2 * (size_t)src, ra, rb);
+        const float4 t = pool.thr[src], pe = pool.pend[src], sh = pool.sh_d[src];
+        st_rec(pool.od + 2 * (size_t)dst, o, d);
+        st_rec(pool.rs + 2 * (size_t)dst, ra, rb);
         pool.thr[dst] = t;
-        pool.rad[dst] = r;
         pool.pend[dst] = pe;
         pool.sh_d[dst] = sh;
-        pool.rng_a[dst] = ra;
-        pool.rng_b[dst] = rb;
     }
 }
 
@@ -147,53 +148,9 @@ __global__ void k_compact_commit(Control* ctl) {
 __global__ void k_init_pool(PoolView pool) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool.capacity) return;
-    pool.ray_d[i] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
-    pool.sh_d[i] = make_float4(0.f, 0.f, 0.f, i2f(0));
+    st_rec(pool.od + 2 * (size_t)i, make_float4(0.f, 0.f, 0.f, 0.f),  // no shadow ray
+           make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC))));
     if (pool.dead_mask && (i & 31) == 0) pool.dead_mask[i >> 5] = 0xffffffffu;
-}
-
-// ---- free scan: dead-mask words of the last shade pass -> free list ----------------------------
-// One thread per mask word (32 slots).  Block-level exclusive scan of the popcounts, one global atomic
-// per block on Control::n_free, then every thread writes the slots of its set bits.  The shade kernel
-// itself appends nothing (no block barrier, no atomic round trip on its critical path).
-constexpr int kScanBlock = 256;
-__global__ void __launch_bounds__(kScanBlock) k_free_scan(const uint32_t* __restrict__ dead_mask, int* __restrict__ free_list,
-                                                          Control* ctl) {
-    __shared__ int warp_sum[kScanBlock / 32];
-    __shared__ int block_base;
-    const int n_words = (ctl->active_cap + 31) >> 5;
-    const int w = blockIdx.x * kScanBlock + threadIdx.x;
-    if (blockIdx.x * kScanBlock >= n_words) return;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t m = w < n_words ? dead_mask[w] : 0u;
-    const int c = __popc(m);
-    int incl = c;  // inclusive scan within the warp
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)lane >= d) incl += v;
-    }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int ws = (int)lane < kScanBlock / 32 ? warp_sum[lane] : 0;
-        int wi = ws;
-#pragma unroll
-        for (int d = 1; d < kScanBlock / 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, wi, d);
-            if ((int)lane >= d) wi += v;
-        }
-        if ((int)lane < kScanBlock / 32) warp_sum[lane] = wi - ws;  // exclusive prefix of the warp totals
-        if (lane == kScanBlock / 32 - 1) block_base = wi ? atomicAdd(&ctl->n_free, wi) : 0;
-    }
-    __syncthreads();
-    int at = block_base + warp_sum[warp] + incl - c;
-    const int first = w << 5;
-    while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        free_list[at++] = first + b;
-    }
 }
 
 // ---- XORWOW column table: col_vecs[f*w + col] = M^col * v0(frame f) --------------------
@@ -234,31 +191,6 @@ TRT_DEV Xorwow sample_rng(const JobParams& job, int f, int row, int col) {
     return s;
 }
 
-// ---- regenerate: refill freed slots with the next camera samples ----------------------
-__global__ void __launch_bounds__(kBlock, 6) k_regen(PoolView pool, const int* __restrict__ free_list,
-                                                  const Control* __restrict__ ctl, JobParams job) {
-    const int n = ctl->n_regen;
-    const unsigned long long base = ctl->regen_base;
-    const unsigned pixels = (unsigned)(job.rc.width * job.rc.height);
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const int slot = free_list[j];
-        const unsigned long long s = base + (unsigned long long)j;
-        const int f = (int)(s / pixels);
-        const int pix = (int)(s % pixels);              // reference pixel index i
-        const int row = pix / job.rc.width, col = pix - row * job.rc.width;
-        const int y = job.rc.height - 1 - row;          // i = (h-1-y)*w + x  (reference :322)
-        Xorwow rng = sample_rng(job, f, row, col);
-        const Ray r = primary_ray(job.cam, col, y, job.rc.width, job.rc.height, rng);
-        // a fresh path has throughput 1 and no radiance: neither array is written (scattered 16-byte
-        // stores cost a read-modify-write of the 32-byte sector); the pixel index rides in ray_o.w,
-        // which only carries a shadow-ray length from depth 1 on, until shade moves it to thr.w
-        pool.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, i2f(pix));
-        pool.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
-        pool.rng_a[slot] = make_uint4(rng.v0, rng.v1, rng.v2, rng.v3);
-        pool.rng_b[slot] = make_uint2(rng.v4, rng.d);
-    }
-}
-
 // ---- refill: free scan + bookkeeping + regeneration in ONE kernel ------------------------------
 // One thread per dead-mask word (32 slots), kRefillBlock words per block.  A block
 //   1. scans its mask words (the slots that ended in the last shade pass) into a slot list in shared memory,
@@ -294,8 +226,8 @@ TRT_DEV void xw_matvec_planes(const uint32_t* __restrict__ tab, const uint32_t i
     out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4;
 }
 
-__global__ void __launch_bounds__(kRefillBlock) k_refill(PoolView pool, Control* ctl, JobParams job, int compact_quarters,
-                                                         int samples_left) {
+__global__ void __launch_bounds__(kRefillBlock, 4) k_refill(PoolView pool, Control* ctl, JobParams job, int compact_quarters,
+                                                            int samples_left, int debug) {
     __shared__ uint32_t s_tab[2][5 * kXwWindowEntries];
     __shared__ uint16_t s_list[kRefillSlots];
     __shared__ int s_warp[kRefillBlock / 32];
@@ -415,13 +347,18 @@ __global__ void __launch_bounds__(kRefillBlock) k_refill(PoolView pool, Control*
                     rng.v0 = o[0]; rng.v1 = o[1]; rng.v2 = o[2]; rng.v3 = o[3]; rng.v4 = o[4];
                     rng.d = cb.y;
                     const Ray ray = primary_ray(job.cam, col, y, job.rc.width, job.rc.height, rng);
-                    // a fresh path has throughput 1 and no radiance: neither array is written (scattered 16-byte
-                    // stores cost a read-modify-write of the 32-byte sector); the pixel index rides in ray_o.w,
-                    // which only carries a shadow-ray length from depth 1 on, until shade moves it to thr.w
-                    pool.ray_o[slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, i2f(pix));
-                    pool.ray_d[slot] = make_float4(ray.d.x, ray.d.y, ray.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
-                    pool.rng_a[slot] = make_uint4(rng.v0, rng.v1, rng.v2, rng.v3);
-                    pool.rng_b[slot] = make_uint2(rng.v4, rng.d);
+                    if (debug) {  // the slot must have ended (dead, no shadow ray waiting) and lie inside the visited prefix
+                        const bool ok = (f2i(pool.od[2 * slot + 1].w) & 0xff) == SLOT_DEAD && !(pool.od[2 * slot].w > 0.f) && slot < cap;
+                        if (!ok) atomicAdd(&ctl->cnt_violations, 1ull);
+                    }
+                    // Two full 32-byte sectors per fresh path (a 16-byte store into a sector nobody else is writing
+                    // costs a read-modify-write of the sector).  A fresh path has throughput 1 and no radiance:
+                    // thr / pend are not written; the pixel index rides in od[2s].w with the sign bit set (that word
+                    // carries a shadow-ray length from depth 1 on, and "> 0" means "trace it") until shade moves it
+                    // to thr.w
+                    st_rec(pool.od + 2 * (size_t)slot, make_float4(ray.o.x, ray.o.y, ray.o.z, i2f(pix | kFreshPixelBit)),
+                           make_float4(ray.d.x, ray.d.y, ray.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC))));
+                    st_rec(pool.rs + 2 * (size_t)slot, make_uint4(rng.v0, rng.v1, rng.v2, rng.v3), make_uint4(rng.v4, rng.d, 0u, 0u));
                 }
             }
         }
@@ -464,15 +401,22 @@ TRT_DEV void warp_add(unsigned long long* counter, unsigned v) {
     if ((threadIdx.x & 31u) == 0 && total) atomicAdd(counter, (unsigned long long)total);
 }
 
+// an occluded shadow ray cancels the next-event contribution waiting in pend.xyz (pend.w is radiance.z: it stays)
+TRT_DEV void cancel_pend(const PoolView& pool, int slot) {
+    float* p = reinterpret_cast<float*>(pool.pend + slot);
+    __stcs(reinterpret_cast<float2*>(p), make_float2(0.f, 0.f));
+    __stcs(p + 2, 0.f);
+}
+
 // ---- extend, reference order: closest hit for every active slot --------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev sc, Control* ctl) {
     unsigned nodes = 0, tris = 0, rays = 0;
     const int cap = min(pool.capacity, ctl->active_cap);
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < cap; slot += gridDim.x * blockDim.x) {
-        const float4 d4 = pool.ray_d[slot];
+        const float4 d4 = pool.od[2 * slot + 1];
         if ((f2i(d4.w) & 0xff) != SLOT_ACTIVE) continue;
-        const float4 o4 = pool.ray_o[slot];
+        const float4 o4 = pool.od[2 * slot];
         Ray r;
         r.o = f3(o4.x, o4.y, o4.z);
         r.d = f3(d4.x, d4.y, d4.z);
@@ -505,14 +449,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_shade(PoolView pool, Control* c
     // sized by the host's bound, every slot below it is valid memory): a dependent read of the control block
     // first cost every CTA an L2 round trip before its first state load.  `eager` is the host's knowledge
     // (samples are still being handed out, the pool is mostly live).
-    const float4 d4 = pool.ray_d[slot];
-    float4 thr4, rad4, pend4, o4;
+    float4 o4, d4;
+    ld_rec(pool.od + 2 * (size_t)slot, o4, d4);
+    float4 thr4, pend4;
     float2 hit;
-    uint4 ra;
-    uint2 rb;
+    uint4 ra, rb;
     if (eager) {
-        thr4 = pool.thr[slot]; rad4 = pool.rad[slot]; pend4 = pool.pend[slot]; o4 = pool.ray_o[slot];
-        hit = pool.hit[slot]; ra = pool.rng_a[slot]; rb = pool.rng_b[slot];
+        thr4 = pool.thr[slot]; pend4 = pool.pend[slot];
+        hit = pool.hit[slot]; ld_rec(pool.rs + 2 * (size_t)slot, ra, rb);
     }
     const int cap = ctl->active_cap;                         // a multiple of the block size
     if (blockIdx.x * blockDim.x >= cap) return;              // whole block beyond the visited prefix
@@ -521,17 +465,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_shade(PoolView pool, Control* c
     bool terminated = false;
     if (state != SLOT_DEAD) {
         if (!eager) {
-            thr4 = pool.thr[slot]; rad4 = pool.rad[slot]; pend4 = pool.pend[slot]; o4 = pool.ray_o[slot];
-            hit = pool.hit[slot]; ra = pool.rng_a[slot]; rb = pool.rng_b[slot];
+            thr4 = pool.thr[slot]; pend4 = pool.pend[slot];
+            hit = pool.hit[slot]; ld_rec(pool.rs + 2 * (size_t)slot, ra, rb);
         }
         PathVertexIO io;
         io.shadow = false;
         io.depth = (flags >> 8) & 0xff;
-        const bool fresh = io.depth == 0;  // regenerate leaves thr / rad unwritten and the pixel in ray_o.w
-        const int pix = fresh ? f2i(o4.w) : f2i(thr4.w);
+        const bool fresh = io.depth == 0;  // refill leaves thr / pend unwritten and the pixel in od[2s].w
+        const int pix = fresh ? (f2i(o4.w) & ~kFreshPixelBit) : f2i(thr4.w);
         io.thr = fresh ? f3(1.f, 1.f, 1.f) : f3(thr4.x, thr4.y, thr4.z);
-        io.rad = fresh ? f3(0.f, 0.f, 0.f) : f3(rad4.x, rad4.y, rad4.z);
-        // next-event estimate of the previous vertex; the shadow kernel zeroed it if occluded
+        // radiance: .x .y ride behind the RNG state, .z behind the pending contribution
+        io.rad = fresh ? f3(0.f, 0.f, 0.f) : f3(__uint_as_float(rb.z), __uint_as_float(rb.w), pend4.w);
+        // next-event estimate of the previous vertex; the shadow pass zeroed it if occluded
         if (io.depth > 0) io.rad = v_add(io.rad, f3(pend4.x, pend4.y, pend4.z));
         if (state == SLOT_ACTIVE) {
             float t_hit = hit.x;
@@ -555,20 +500,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_shade(PoolView pool, Control* c
                     // shadow ray in flight is finalised one iteration later (SLOT_FINISH)
                     const int ns = depth >= job.rc.max_depth ? SLOT_FINISH : SLOT_ACTIVE;
                     // the shadow ray starts where the next ray starts (x_hit + nl * 1e-3, reference
-                    // :692 and :731): its length rides in ray_o.w, its direction in sh_d
-                    pool.ray_o[slot] = make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, io.shadow ? io.shadow_max_dist : 0.f);
-                    pool.ray_d[slot] = make_float4(io.ray.d.x, io.ray.d.y, io.ray.d.z,
-                                                   i2f(pack_flags(ns, depth, io.prev_mode)));
+                    // :692 and :731): its length rides in od[2s].w (0 = none), its direction in sh_d
+                    st_rec(pool.od + 2 * (size_t)slot, make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, io.shadow ? io.shadow_max_dist : 0.f),
+                           make_float4(io.ray.d.x, io.ray.d.y, io.ray.d.z, i2f(pack_flags(ns, depth, io.prev_mode))));
                     pool.thr[slot] = make_float4(io.thr.x, io.thr.y, io.thr.z, i2f(pix));
-                    pool.rad[slot] = make_float4(io.rad.x, io.rad.y, io.rad.z, 0.f);
-                    pool.rng_a[slot] = make_uint4(io.rng.v0, io.rng.v1, io.rng.v2, io.rng.v3);
-                    pool.rng_b[slot] = make_uint2(io.rng.v4, io.rng.d);
+                    st_rec(pool.rs + 2 * (size_t)slot, make_uint4(io.rng.v0, io.rng.v1, io.rng.v2, io.rng.v3),
+                           make_uint4(io.rng.v4, io.rng.d, __float_as_uint(io.rad.x), __float_as_uint(io.rad.y)));
                     if (io.shadow) {
-                        pool.pend[slot] = make_float4(io.shadow_contrib.x, io.shadow_contrib.y, io.shadow_contrib.z, 0.f);
-                        pool.sh_d[slot] = make_float4(io.shadow_ray.d.x, io.shadow_ray.d.y, io.shadow_ray.d.z, i2f(1));
+                        pool.pend[slot] = make_float4(io.shadow_contrib.x, io.shadow_contrib.y, io.shadow_contrib.z, io.rad.z);
+                        pool.sh_d[slot] = make_float4(io.shadow_ray.d.x, io.shadow_ray.d.y, io.shadow_ray.d.z, 0.f);
                     } else {
-                        pool.pend[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        pool.sh_d[slot] = make_float4(0.f, 0.f, 0.f, i2f(0));
+                        pool.pend[slot] = make_float4(0.f, 0.f, 0.f, io.rad.z);
                     }
                 }
             }
@@ -583,11 +525,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_shade(PoolView pool, Control* c
                 atomicAdd(a + 1, rad.y);
                 atomicAdd(a + 2, rad.z);
             }
-            pool.ray_d[slot] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
-            pool.sh_d[slot] = make_float4(0.f, 0.f, 0.f, i2f(0));
+            // one full sector: no shadow ray, slot dead
+            st_rec(pool.od + 2 * (size_t)slot, make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC))));
         }
     }
-    // which slots ended: one mask word per warp (all 32 lanes are here); k_free_scan lists them
+    // which slots ended: one mask word per warp (all 32 lanes are here); k_refill turns them into fresh paths
     const unsigned ended = __ballot_sync(0xffffffffu, terminated);
     if ((threadIdx.x & 31u) == 0) pool.dead_mask[slot >> 5] = ended;
 }
@@ -598,9 +540,9 @@ __global__ void __launch_bounds__(kBlock) k_shadow_ref(PoolView pool, SceneDev s
     unsigned nodes = 0, tris = 0, rays = 0;
     const int cap = min(pool.capacity, ctl->active_cap);
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < cap; slot += gridDim.x * blockDim.x) {
+        const float4 o4 = pool.od[2 * slot];
+        if (!(o4.w > 0.f)) continue;  // no shadow ray in this slot
         const float4 d4 = pool.sh_d[slot];
-        if (f2i(d4.w) != 1) continue;
-        const float4 o4 = pool.ray_o[slot];
         Ray r;
         r.o = f3(o4.x, o4.y, o4.z);
         r.d = f3(d4.x, d4.y, d4.z);
@@ -608,7 +550,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow_ref(PoolView pool, SceneDev s
         const bool occluded = ref_shadow<COUNT>(sc, r, o4.w, &vc);
         if (COUNT) { nodes += vc.fetched; tris += vc.tris; }
         rays++;
-        if (occluded) pool.pend[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (occluded) cancel_pend(pool, slot);
     }
     warp_add(&ctl->cnt_shadow, rays);
     if (COUNT) {
@@ -653,6 +595,7 @@ struct Feeder {  // warp-uniform state of the staging double buffer
     bool nxt_req;  // a bulk copy into the other buffer has been issued
     bool drained;  // the global cursor ran past the pool
     unsigned phase;  // bit b = parity the next wait on buffer b uses
+    float4 cur_sh, nxt_sh;  // any-hit work: this lane's shadow direction of the current / the requested chunk
 };
 
 TRT_DEV void feeder_init(Feeder& f) {
@@ -664,30 +607,37 @@ TRT_DEV void feeder_init(Feeder& f) {
     f.nxt_req = false;
     f.drained = false;
     f.phase = 0;
+    f.cur_sh = f.nxt_sh = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 TRT_DEV bool feeder_exhausted(const Feeder& f) { return f.drained && !f.fresh && !f.nxt_req; }
 
 // Make the next chunk current if it has landed (or wait for it when `block`: nobody in the warp
-// has anything else to do), and keep one chunk in flight behind it.
-TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const float4* src_o, const float4* src_d,
+// has anything else to do), and keep one chunk in flight behind it.  A chunk is the 32 origin/direction
+// records of 32 consecutive slots: ONE bulk copy of 1 KB.  SHADOW: the any-hit work reads the origin (and the
+// shadow length in its .w) from the same records and the shadow direction from sh_d; that vector is fetched by
+// the lanes themselves (a coalesced 512-byte load) when the chunk is requested and waits in a register, so the
+// staging buffers stay at 1 KB per chunk.
+template <bool SHADOW>
+TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const float4* src_od, const float4* src_sh,
                             int* cursor, int limit, unsigned lane, bool block) {
     if (!f.fresh && f.nxt_req) {
         const int nb = f.cur_buf ^ 1;
         const uint32_t parity = (f.phase >> nb) & 1u;
-        int ready = 0;
-        if (lane == 0) {
-            ready = mbar_try_wait(&bars[nb], parity) ? 1 : 0;
-            if (block) {
-                while (!ready) ready = mbar_try_wait(&bars[nb], parity) ? 1 : 0;
-            }
+        // every lane polls (one converged instruction, no branch around a single-lane section); the vote makes the
+        // answer warp-uniform should the phase flip between two lanes' reads
+        bool ready = mbar_try_wait(&bars[nb], parity);
+        if (block) {
+            while (!__all_sync(0xffffffffu, ready)) ready = mbar_try_wait(&bars[nb], parity);
+        } else {
+            ready = __all_sync(0xffffffffu, ready);
         }
-        ready = __shfl_sync(0xffffffffu, ready, 0);
         if (ready) {
             f.phase ^= 1u << nb;
             f.cur_buf = nb;
             f.cur_base = f.nxt_base;
             f.fresh = true;
             f.nxt_req = false;
+            if (SHADOW) f.cur_sh = f.nxt_sh;
         }
     }
     if (!f.nxt_req && !f.drained) {
@@ -705,11 +655,10 @@ TRT_DEV void feeder_advance(Feeder& f, float4* stage, uint64_t* bars, const floa
         } else {
             const int nb = f.cur_buf ^ 1;  // the buffer not being read
             if (lane == 0) {
-                float4* dst = stage + nb * (2 * kChunk);
                 mbar_expect_tx(&bars[nb], 2 * kChunk * 16);
-                bulk_g2s(dst, src_o + base, kChunk * 16, &bars[nb]);
-                bulk_g2s(dst + kChunk, src_d + base, kChunk * 16, &bars[nb]);
+                bulk_g2s(stage + nb * (2 * kChunk), src_od + 2 * (size_t)base, 2 * kChunk * 16, &bars[nb]);
             }
+            if (SHADOW) f.nxt_sh = __ldg(src_sh + base + lane);
             f.nxt_req = true;
             f.nxt_base = base;
         }
@@ -749,11 +698,11 @@ TRT_DEV void extend_phase(const PoolView& pool, const SceneDev& sc, const TopPri
         unsigned act = __ballot_sync(0xffffffffu, has);
         // 1. top phase on fresh chunks while the queue has room for a whole chunk
         while (qn <= kQueueLow && !feeder_exhausted(fd)) {
-            feeder_advance(fd, stage, bars, pool.ray_o, pool.ray_d, &ctl->cursor_extend, slot_limit, lane,
-                           act == 0 && qn == 0);
+            feeder_advance<false>(fd, stage, bars, pool.od, nullptr, &ctl->cursor_extend, slot_limit, lane,
+                                  act == 0 && qn == 0);
             if (!fd.fresh) break;  // the next chunk has not landed: traverse meanwhile
             const float4* buf = stage + fd.cur_buf * (2 * kChunk);
-            const float4 o4 = buf[lane], d4 = buf[kChunk + lane];
+            const float4 o4 = buf[2 * lane], d4 = buf[2 * lane + 1];
             const bool live = (f2i(d4.w) & 0xff) == SLOT_ACTIVE;
             const int my_slot = fd.cur_base + (int)lane;
             TopResult tr = ph.ranked_top ? top_closest_ranked(top, s_top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), live)
@@ -862,17 +811,17 @@ TRT_DEV void shadow_phase(const PoolView& pool, const SceneDev& sc, const TopPri
     for (;;) {
         unsigned act = __ballot_sync(0xffffffffu, has);
         while (qn <= kQueueLow && !feeder_exhausted(fd)) {
-            feeder_advance(fd, stage, bars, pool.ray_o, pool.sh_d, &ctl->cursor_shadow, slot_limit, lane,
-                           act == 0 && qn == 0);
+            feeder_advance<true>(fd, stage, bars, pool.od, pool.sh_d, &ctl->cursor_shadow, slot_limit, lane,
+                                 act == 0 && qn == 0);
             if (!fd.fresh) break;
             const float4* buf = stage + fd.cur_buf * (2 * kChunk);
-            const float4 o4 = buf[lane], d4 = buf[kChunk + lane];
-            const bool live = f2i(d4.w) == 1;
+            const float4 o4 = buf[2 * lane], d4 = fd.cur_sh;
+            const bool live = o4.w > 0.f;  // a shadow ray waits in this slot
             const int my_slot = fd.cur_base + (int)lane;
             const int verdict = top_shadow(top, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), o4.w, live);
             if (live) rays++;
             // the next-event contribution waits in pend; an occluded ray cancels it
-            if (live && verdict == 1) __stcs(&pool.pend[my_slot], make_float4(0.f, 0.f, 0.f, 0.f));
+            if (live && verdict == 1) cancel_pend(pool, my_slot);
             const bool tree = live && verdict == 2;
             const unsigned m = __ballot_sync(0xffffffffu, tree);
             if (tree) {
@@ -921,7 +870,7 @@ TRT_DEV void shadow_phase(const PoolView& pool, const SceneDev& sc, const TopPri
         }
         if (has && shadow_done<E, S>(st, stk_base)) {
             // the next-event contribution waits in pend; an occluded ray cancels it
-            if (st.occluded) __stcs(&pool.pend[slot], make_float4(0.f, 0.f, 0.f, 0.f));
+            if (st.occluded) cancel_pend(pool, slot);
             st.np = stk_base;  // an occluded ray leaves entries behind
             st.tp = stk_ttop;
             st.nspill = 0;
@@ -1072,7 +1021,7 @@ TRT_DEV bool finish_wanted(const Control* ctl, int finish_below) {
     return ctl->active_cap > 0 && ctl->alive <= finish_below && ctl->next_sample >= ctl->total_samples;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool WIDE>
 __global__ void __launch_bounds__(kFinishBlock) k_finish_paths(PoolView pool, Control* ctl, SceneDev sc,
                                                                const __grid_constant__ TopPrims top, JobParams job,
                                                                int finish_below) {
@@ -1096,7 +1045,7 @@ __global__ void __launch_bounds__(kFinishBlock) k_finish_paths(PoolView pool, Co
             ShadowRay st;
             shadow_begin(st, make_float4(o.x, o.y, o.z, max_dist), make_float4(d.x, d.y, d.z, 0.f), stk_base, stk_ttop, E);
             while (!shadow_done<E, S>(st, stk_base)) {
-                shadow_node_step<E, S, COUNT, false>(nullptr, 0, sc, st, stk_base, spill, &wc);
+                shadow_node_step<E, S, COUNT, WIDE>(nullptr, 0, sc, st, stk_base, spill, &wc);
                 shadow_tri_step<E, S, COUNT>(sc, st, stk_base, &wc);
             }
             occ = st.occluded;
@@ -1106,7 +1055,7 @@ __global__ void __launch_bounds__(kFinishBlock) k_finish_paths(PoolView pool, Co
     };
     for (int first = blockIdx.x * kFinishBlock; first < cap; first += gridDim.x * kFinishBlock) {
         const int slot = first + (int)threadIdx.x;  // cap is a multiple of the block size
-        const float4 d4 = pool.ray_d[slot];
+        const float4 d4 = pool.od[2 * slot + 1];
         const int flags = f2i(d4.w);
         const int state = flags & 0xff;
         bool active = state == SLOT_ACTIVE;
@@ -1127,24 +1076,26 @@ __global__ void __launch_bounds__(kFinishBlock) k_finish_paths(PoolView pool, Co
         F3 sh_dir = f3(0.f, 0.f, 0.f);
         float sh_len = 0.f;
         if (live) {
-            const float4 o4 = pool.ray_o[slot];
-            const bool fresh = io.depth == 0;  // regenerate leaves thr / rad unwritten and the pixel in ray_o.w
+            const float4 o4 = pool.od[2 * slot];
+            const uint4 ra = pool.rs[2 * slot], rb = pool.rs[2 * slot + 1];
+            const bool fresh = io.depth == 0;  // refill leaves thr / pend unwritten and the pixel in od[2s].w
             io.ray.o = f3(o4.x, o4.y, o4.z);
             io.ray.d = f3(d4.x, d4.y, d4.z);
             if (fresh) {
-                pix = f2i(o4.w);
+                pix = f2i(o4.w) & ~kFreshPixelBit;
             } else {
-                const float4 thr4 = pool.thr[slot], rad4 = pool.rad[slot], pend4 = pool.pend[slot], sh4 = pool.sh_d[slot];
+                const float4 thr4 = pool.thr[slot], pend4 = pool.pend[slot];
                 pix = f2i(thr4.w);
                 io.thr = f3(thr4.x, thr4.y, thr4.z);
-                io.rad = f3(rad4.x, rad4.y, rad4.z);
+                io.rad = f3(__uint_as_float(rb.z), __uint_as_float(rb.w), pend4.w);
                 pend = f3(pend4.x, pend4.y, pend4.z);
-                sh = f2i(sh4.w) == 1;
-                sh_dir = f3(sh4.x, sh4.y, sh4.z);
-                sh_len = o4.w;
+                sh = o4.w > 0.f;
+                if (sh) {
+                    const float4 sh4 = pool.sh_d[slot];
+                    sh_dir = f3(sh4.x, sh4.y, sh4.z);
+                    sh_len = o4.w;
+                }
             }
-            const uint4 ra = pool.rng_a[slot];
-            const uint2 rb = pool.rng_b[slot];
             io.rng.v0 = ra.x; io.rng.v1 = ra.y; io.rng.v2 = ra.z; io.rng.v3 = ra.w;
             io.rng.v4 = rb.x; io.rng.d = rb.y;
         }
@@ -1166,7 +1117,7 @@ __global__ void __launch_bounds__(kFinishBlock) k_finish_paths(PoolView pool, Co
                     closest_begin(st, make_float4(io.ray.o.x, io.ray.o.y, io.ray.o.z, 0.f),
                                   make_float4(io.ray.d.x, io.ray.d.y, io.ray.d.z, 0.f), tr.d_min, tr.id, stk_base, stk_ttop);
                     while (!closest_done<E, S>(st, stk_base)) {
-                        closest_node_step<E, S, COUNT, false>(nullptr, 0, sc, st, stk_base, spill, &wc);
+                        closest_node_step<E, S, COUNT, WIDE>(nullptr, 0, sc, st, stk_base, spill, &wc);
                         closest_tri_step2<E, S, COUNT>(sc, st, stk_base, &wc);
                     }
                     t_hit = st.d_min;
@@ -1219,21 +1170,119 @@ __global__ void k_finish_commit(Control* ctl, int finish_below) {
     ctl->compact_go = 0;
 }
 
+// ---- 128-byte nodes -> compressed 64-byte nodes (traverse_fast.cuh CNode) -------------------------
+// One thread per node.  Per axis: the grid spans the union of the children's boxes with a power-of-two step,
+// base is pushed down until plane(0) <= the smallest lo plane, and every child's lo / hi byte is moved outward
+// until the plane the TRAVERSAL will decode from it (the same p_fma expression, cnode_plane) contains the
+// original plane; if 255 steps do not reach the largest hi plane the step doubles.  The step is also kept
+// above four ulps of the largest coordinate so that rounding cannot collapse the grid.
+TRT_DEV float cnode_decode(int q, float scale, float base) {
+    return p_fma(__uint_as_float(0x4B000000u | (uint32_t)q), scale, base);
+}
+
+__global__ void __launch_bounds__(kBlock) k_compress_nodes(const float4* __restrict__ wide, int n, CNode* __restrict__ out,
+                                                           int* __restrict__ n_bad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* w = wide + (size_t)i * 8;
+    const int4 ch = *reinterpret_cast<const int4*>(w + 6);
+    const int child[4] = {ch.x, ch.y, ch.z, ch.w};
+    CNode c;
+    uint32_t qw[6] = {0, 0, 0, 0, 0, 0};
+    bool bad = false;
+    for (int a = 0; a < 3; a++) {
+        const float4 lo4 = w[2 * a], hi4 = w[2 * a + 1];
+        const float lo[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, hi[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+        float mn = 3.0e38f, mx = -3.0e38f;
+        for (int k = 0; k < 4; k++)
+            if (child[k] != kWideEmptyRef) { mn = fminf(mn, lo[k]); mx = fmaxf(mx, hi[k]); }
+        if (!(mn <= mx)) { mn = 0.f; mx = 0.f; }  // no children (an empty tree's root)
+        // power-of-two step: covers the extent in 254 steps, and at least 4 ulps of the largest coordinate
+        const float big = fmaxf(fmaxf(fabsf(mn), fabsf(mx)), 1e-30f);
+        int e_min;
+        frexpf(big, &e_min);           // big = m * 2^e_min, m in [0.5, 1): ulp(big) = 2^(e_min - 24)
+        int e = e_min - 24 + 2;
+        const float ext = mx - mn;
+        if (ext > 0.f) {
+            int ee;
+            frexpf(ext / 254.f, &ee);  // ext / 254 <= 2^ee
+            e = max(e, ee);
+        }
+        float scale, base;
+        int qlo[4], qhi[4];
+        for (int tries = 0;; tries++) {
+            scale = ldexpf(1.f, e);
+            base = p_fma(-8388608.f, scale, mn);
+            for (int it = 0; it < 64 && cnode_decode(0, scale, base) > mn; it++) base = nextafterf(base, -3.0e38f);
+            bool ok = cnode_decode(0, scale, base) <= mn && cnode_decode(255, scale, base) >= mx;
+            const float origin = cnode_decode(0, scale, base);
+            for (int k = 0; k < 4 && ok; k++) {
+                if (child[k] == kWideEmptyRef) { qlo[k] = 255; qhi[k] = 0; continue; }
+                int ql = min(255, max(0, (int)floorf((lo[k] - origin) / scale)));
+                while (ql > 0 && cnode_decode(ql, scale, base) > lo[k]) ql--;
+                int qh = min(255, max(0, (int)ceilf((hi[k] - origin) / scale)));
+                while (qh < 255 && cnode_decode(qh, scale, base) < hi[k]) qh++;
+                ok = cnode_decode(ql, scale, base) <= lo[k] && cnode_decode(qh, scale, base) >= hi[k];
+                qlo[k] = ql;
+                qhi[k] = qh;
+            }
+            if (ok) break;
+            if (tries == 40) { bad = true; break; }
+            e++;
+        }
+        c.base[a] = base;
+        c.scale[a] = scale;
+        for (int k = 0; k < 4; k++) {
+            qw[2 * a] |= (uint32_t)qlo[k] << (8 * k);
+            qw[2 * a + 1] |= (uint32_t)qhi[k] << (8 * k);
+        }
+    }
+    c.qx_lo = qw[0]; c.qx_hi = qw[1]; c.qy_lo = qw[2]; c.qy_hi = qw[3]; c.qz_lo = qw[4]; c.qz_hi = qw[5];
+    for (int k = 0; k < 4; k++) c.child[k] = child[k];
+    out[i] = c;
+    if (bad) atomicAdd(n_bad, 1);
+}
+
+// ---- instancing: one parsed mesh, many placements -> the object array the reference's loader would build -------
+// out[(i * n_unit + j)] = unit[j] with its three vertices moved to fma(v, scale_i, offset_i): the arithmetic of the
+// reference's load_obj (src/loader.cpp:51: v * scale + offset, contracted to one FMA by its -O3 x86 build and
+// written as fmaf in host/loader.cpp), so the records equal, byte for byte, what one load_obj call per instance
+// produces -- without parsing the file n_instances times and without the array ever existing on the host.
+__global__ void __launch_bounds__(kBlock) k_instance_objects(const float4* __restrict__ unit, int n_unit,
+                                                             const float4* __restrict__ inst, int n_inst,
+                                                             float4* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per float4 of the output
+    const long long total = (long long)n_unit * n_inst * 7;
+    if (t >= total) return;
+    const long long rec = t / 7;
+    const int part = (int)(t - rec * 7);
+    const int i = (int)(rec / n_unit), j = (int)(rec - (long long)i * n_unit);
+    float4 v = __ldg(unit + (size_t)j * 7 + part);
+    if (part < 3) {  // v0, v1, v2 (the fourth lane is padding and stays as it is)
+        const float4 p = __ldg(inst + i);
+        v.x = __fmaf_rn(v.x, p.w, p.x);
+        v.y = __fmaf_rn(v.y, p.w, p.y);
+        v.z = __fmaf_rn(v.z, p.w, p.z);
+    }
+    out[t] = v;
+}
+
 // ---- parity / test entry points -------------------------------------------------------------
 // primary rays of one frame into a scratch pool (slot = reference pixel index)
 __global__ void __launch_bounds__(kBlock) k_pack_primary(PoolView pool, JobParams job, float* out_ray) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= pool.capacity) return;
     if (pix >= job.rc.width * job.rc.height) {
-        pool.ray_d[pix] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
+        pool.od[2 * pix] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pool.od[2 * pix + 1] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
         return;
     }
     const int row = pix / job.rc.width, col = pix - row * job.rc.width;
     const int y = job.rc.height - 1 - row;
     Xorwow rng = sample_rng(job, 0, row, col);
     const Ray r = primary_ray(job.cam, col, y, job.rc.width, job.rc.height, rng);
-    pool.ray_o[pix] = make_float4(r.o.x, r.o.y, r.o.z, 0.f);
-    pool.ray_d[pix] = make_float4(r.d.x, r.d.y, r.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
+    pool.od[2 * pix] = make_float4(r.o.x, r.o.y, r.o.z, 0.f);
+    pool.od[2 * pix + 1] = make_float4(r.d.x, r.d.y, r.d.z, i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
     if (out_ray) {
         float* p = out_ray + (size_t)pix * 6;
         p[0] = r.o.x; p[1] = r.o.y; p[2] = r.o.z; p[3] = r.d.x; p[4] = r.d.y; p[5] = r.d.z;
@@ -1241,19 +1290,19 @@ __global__ void __launch_bounds__(kBlock) k_pack_primary(PoolView pool, JobParam
 }
 
 // caller-provided rays (8 floats: o.xyz, d.xyz, t_max, unused) into a scratch pool, as closest-hit
-// rays and as shadow rays at once
+// rays and as shadow rays at once (a shadow ray needs t_max > 0: that word is also the "trace it" flag)
 __global__ void __launch_bounds__(kBlock) k_pack_rays(PoolView pool, const float* __restrict__ rays, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= pool.capacity) return;
     if (i >= n) {
-        pool.ray_d[i] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
-        pool.sh_d[i] = make_float4(0.f, 0.f, 0.f, i2f(0));
+        pool.od[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pool.od[2 * i + 1] = make_float4(0.f, 0.f, 0.f, i2f(pack_flags(SLOT_DEAD, 0, MODE_SPEC)));
         return;
     }
     const float* p = rays + (size_t)i * 8;
-    pool.ray_o[i] = make_float4(p[0], p[1], p[2], p[6]);
-    pool.ray_d[i] = make_float4(p[3], p[4], p[5], i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
-    pool.sh_d[i] = make_float4(p[3], p[4], p[5], i2f(1));
+    pool.od[2 * i] = make_float4(p[0], p[1], p[2], p[6]);
+    pool.od[2 * i + 1] = make_float4(p[3], p[4], p[5], i2f(pack_flags(SLOT_ACTIVE, 0, MODE_SPEC)));
+    pool.sh_d[i] = make_float4(p[3], p[4], p[5], 0.f);
     pool.pend[i] = make_float4(1.f, 1.f, 1.f, 0.f);
 }
 
@@ -1264,7 +1313,7 @@ __global__ void __launch_bounds__(kBlock) k_unpack_hits(PoolView pool, SceneDev 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float2 h = pool.hit[i];
-    const float4 o4 = pool.ray_o[i], d4 = pool.ray_d[i];
+    const float4 o4 = pool.od[2 * i], d4 = pool.od[2 * i + 1];
     float t = h.x;
     int id = f2i(h.y);
     const bool replayed = resolve_hit(sc, f3(o4.x, o4.y, o4.z), f3(d4.x, d4.y, d4.z), t, id);
@@ -1378,11 +1427,6 @@ void launch_trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims&
     // the two extra mbarriers per warp come out of the staged nodes
     const int extra_nodes = (int)(((size_t)(THREADS / 32) * 16 + kSmemNodeStride - 1) / kSmemNodeStride);
     const int k = max(0, min(dims.smem_nodes - extra_nodes, sc.n_wide_nodes));
-    if (THREADS == 768 && dims.shadow_pair) {
-        k_trace_fast<768, COUNT, false, true><<<dims.sms, 768, trace_smem_bytes<768>(k), s>>>(
-            pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, dims.shadow_phases);
-        return;
-    }
     k_trace_fast<THREADS, COUNT, false, false><<<dims.sms, THREADS, trace_smem_bytes<THREADS>(k), s>>>(
         pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, dims.shadow_phases);
 }
@@ -1470,8 +1514,6 @@ int wf_configure() {
     rc |= opt_in_smem(k_trace_fast<512, true, false, false>);
     rc |= opt_in_smem(k_trace_fast<768, false, false, false>);
     rc |= opt_in_smem(k_trace_fast<768, true, false, false>);
-    rc |= opt_in_smem(k_trace_fast<768, false, false, true>);
-    rc |= opt_in_smem(k_trace_fast<768, true, false, true>);
     rc |= opt_in_smem(k_trace_fast<1024, false, false, false>);
     rc |= opt_in_smem(k_trace_fast<1024, true, false, false>);
     rc |= opt_in_smem(k_trace_fast<768, false, true, false>);
@@ -1494,9 +1536,7 @@ int wf_fast_max_smem_nodes(int threads, size_t smem_limit) {
     return (int)((smem_limit - fixed) / kSmemNodeStride);
 }
 
-void wf_init_pool(const PoolView& pool, int* free_list, Control* ctl, cudaStream_t s) {
-    (void)ctl;
-    (void)free_list;
+void wf_init_pool(const PoolView& pool, cudaStream_t s) {
     k_init_pool<<<grid_for(pool.capacity), kBlock, 0, s>>>(pool);
 }
 
@@ -1513,72 +1553,45 @@ void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_fra
                                                             seed_base, n_frames, out);
 }
 
-// One iteration.  Side part: prepare -> regenerate.  Main part: [compact] -> extend -> shade -> shadow.
-// With st.overlap the side part of iteration i+1 runs on its own stream as soon as shade(i) is done,
-// i.e. concurrently with shadow(i): regenerate is a latency-bound stream of scattered stores
-// (about a sixth of the slots), the shadow kernel is issue bound and leaves room for one small
-// regenerate CTA per SM, so most of the refill disappears behind the traversal.  The two touch
-// disjoint state: regenerate writes slots that ended in shade(i) (their shadow flag is already
-// cleared), prepare leaves the shadow cursor alone.  Compaction moves slots the shadow kernel reads,
-// so its kernels run on the main stream, behind shadow(i) and the join; prepare only lets it go in an
-// iteration that regenerates nothing, so the order of the two does not matter.
-// Once the job has no samples left (st.samples_left false) there is nothing to overlap and the whole
-// iteration is issued on the main stream.
+// One iteration on one stream: refill -> [compact] -> trace -> shade.
+//   refill : k_refill (free scan + bookkeeping + regeneration of the slots that ended in the last shade pass)
+//   compact: drain phase only (the host launches the three kernels once the job is close to its drain phase;
+//            k_refill lets a compaction go only in an iteration that regenerates nothing)
+//   trace  : FAST, combined -- the shadow rays the last shade pass wrote, then this iteration's closest-hit rays,
+//            one persistent launch (k_trace_fast).  FAST with merged_trace off, and REF: closest hit before
+//            shade, any hit after it, two launches
+//   shade  : one thread per slot
+//   finish : drain tail (combined mode): k_finish_paths + commit ride along once few paths are left
 template <int MODE, bool COUNT>
-static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+static int iteration_impl(const PoolView& pool, Control* ctl, const SceneDev& sc, const TopPrims& top,
                           const JobParams& job, const LaunchDims& dims, const IterStreams& st, cudaEvent_t* marks,
                           int* compact_lists) {
     const int full = pool.capacity / kBlock;
     const int persistent = dims.sms * 8;
-    const bool overlap = st.overlap && st.samples_left && !dims.fused_refill;
-    cudaStream_t s = st.main, side = overlap ? st.side : st.main;
+    cudaStream_t s = st.main;
     int launched = 0;
     // marks[0..5]; st.mark_mask selects which of them are recorded
-    auto mark = [&](int i, cudaStream_t on) { if (marks && ((st.mark_mask >> i) & 1)) cudaEventRecord(marks[i], on); };
-    if (overlap) cudaStreamWaitEvent(side, st.fork, 0);
-    mark(0, side);
+    auto mark = [&](int i) { if (marks && ((st.mark_mask >> i) & 1)) cudaEventRecord(marks[i], s); };
+    mark(0);
     const int visit = min(pool.capacity, st.visit_cap);
-    if (dims.fused_refill) {
-        // free scan + bookkeeping + regeneration of the slots that ended in the last shade pass, one kernel
-        k_refill<<<((visit + 31) / 32 + kRefillBlock - 1) / kRefillBlock, kRefillBlock, 0, s>>>(
-            pool, ctl, job, dims.compact_quarters, st.samples_left ? 1 : 0);
-        launched += 1;
-    } else {
-        // slots that ended in the last shade pass -> free list + count (the count also feeds `alive` in the drain phase)
-        k_free_scan<<<((visit + 31) / 32 + kScanBlock - 1) / kScanBlock, kScanBlock, 0, side>>>(pool.dead_mask, free_list, ctl);
-        k_prepare<<<1, 32, 0, side>>>(ctl, dims.compact_quarters);
-        launched += 2;
-        if (st.samples_left) {
-            // regeneration is a chain of dependent loads per sample: one sample per thread in the steady
-            // state (about a sixth of the pool ends per iteration), grid-stride only when the pool starts up;
-            // small CTAs so that one fits beside the persistent shadow CTA of an SM
-            const int kRegenBlock = dims.regen_block;
-            const int regen_full = (pool.capacity + kRegenBlock - 1) / kRegenBlock;
-            const int regen_blocks = min(regen_full, max(2 * persistent, regen_full / 4));
-            k_regen<<<regen_blocks, kRegenBlock, 0, side>>>(pool, free_list, ctl, job);
-            launched++;
-        }
-    }
-    mark(1, side);
-    if (overlap) {
-        cudaEventRecord(st.join, side);
-        cudaStreamWaitEvent(s, st.join, 0);
-    }
-    if (compact_lists && visit > kCompactMinCap) {  // the host launches these only once the job is close to its drain phase
+    k_refill<<<((visit + 31) / 32 + kRefillBlock - 1) / kRefillBlock, kRefillBlock, 0, s>>>(
+        pool, ctl, job, dims.compact_quarters, st.samples_left ? 1 : 0, dims.debug_checks ? 1 : 0);
+    launched += 1;
+    mark(1);
+    if (compact_lists && visit > kCompactMinCap) {
         int* list_a = compact_lists;
         int* list_b = compact_lists + pool.capacity + 512;  // each list is sized for the whole pool
         k_compact_scan<<<dims.sms * 2, 1024, 0, s>>>(pool, ctl, list_a, list_b);
-        k_compact_move<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b);
+        k_compact_move<<<persistent, kBlock, 0, s>>>(pool, ctl, list_a, list_b, dims.debug_checks ? 1 : 0);
         k_compact_commit<<<1, 32, 0, s>>>(ctl);
         launched += 3;
     }
-    mark(2, s);
-    const bool merged = MODE == TRT_TRAVERSE_FAST && dims.merged_trace && dims.fused_refill;
-    // merged: the shadow rays of the previous shade pass and this iteration's closest-hit rays in one launch
+    mark(2);
+    const bool merged = MODE == TRT_TRAVERSE_FAST && dims.merged_trace;
     if (merged) trace_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else if (MODE == TRT_TRAVERSE_FAST) extend_fast<COUNT>(pool, sc, top, ctl, dims, s);
     else k_extend_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
-    mark(3, s);
+    mark(3);
     // blocks beyond active_cap return at once, but 16 Ki of them still cost 0.1 ms: size the grid by the bound
     const int shade_blocks = (visit + dims.shade_block - 1) / dims.shade_block;
     constexpr bool F = MODE == TRT_TRAVERSE_FAST;
@@ -1593,32 +1606,34 @@ static int iteration_impl(const PoolView& pool, int* free_list, Control* ctl, co
     } else {
         k_shade<COUNT, F, kShadeMaxBlock, 2><<<shade_blocks, dims.shade_block, 0, s>>>(pool, ctl, sc, job, eager);
     }
-    mark(4, s);
-    if (st.overlap && !dims.fused_refill) cudaEventRecord(st.fork, s);  // the next side part may start now
+    launched += 2;
+    mark(4);
     if (!merged) {
         if (MODE == TRT_TRAVERSE_FAST) shadow_fast<COUNT>(pool, sc, top, ctl, dims, s);
         else k_shadow_ref<COUNT><<<full, kBlock, 0, s>>>(pool, sc, ctl);
+        launched += 1;
     }
-    mark(5, s);
+    mark(5);
     if (merged && st.finish_below > 0) {
         // drain tail: once few enough paths are left they are run to completion in one launch (decided on the device)
         const int blocks = max(1, min((visit + kFinishBlock - 1) / kFinishBlock, dims.sms * 16));
-        k_finish_paths<COUNT><<<blocks, kFinishBlock, 0, s>>>(pool, ctl, sc, top, job, st.finish_below);
+        if (dims.wide_loads) k_finish_paths<COUNT, true><<<blocks, kFinishBlock, 0, s>>>(pool, ctl, sc, top, job, st.finish_below);
+        else k_finish_paths<COUNT, false><<<blocks, kFinishBlock, 0, s>>>(pool, ctl, sc, top, job, st.finish_below);
         k_finish_commit<<<1, 32, 0, s>>>(ctl, st.finish_below);
         launched += 2;
     }
-    return launched + (merged ? 2 : 3);
+    return launched;
 }
 
-int wf_iteration(const PoolView& pool, int* free_list, Control* ctl, const SceneDev& sc, const TopPrims& top,
+int wf_iteration(const PoolView& pool, Control* ctl, const SceneDev& sc, const TopPrims& top,
                  const JobParams& job, int traversal, bool count, const LaunchDims& dims, const IterStreams& st,
                  cudaEvent_t* marks, int* compact_lists) {
     if (traversal == TRT_TRAVERSE_REF) {
-        if (count) return iteration_impl<TRT_TRAVERSE_REF, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
-        return iteration_impl<TRT_TRAVERSE_REF, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
+        if (count) return iteration_impl<TRT_TRAVERSE_REF, true>(pool, ctl, sc, top, job, dims, st, marks, compact_lists);
+        return iteration_impl<TRT_TRAVERSE_REF, false>(pool, ctl, sc, top, job, dims, st, marks, compact_lists);
     }
-    if (count) return iteration_impl<TRT_TRAVERSE_FAST, true>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
-    return iteration_impl<TRT_TRAVERSE_FAST, false>(pool, free_list, ctl, sc, top, job, dims, st, marks, compact_lists);
+    if (count) return iteration_impl<TRT_TRAVERSE_FAST, true>(pool, ctl, sc, top, job, dims, st, marks, compact_lists);
+    return iteration_impl<TRT_TRAVERSE_FAST, false>(pool, ctl, sc, top, job, dims, st, marks, compact_lists);
 }
 
 void wf_trace_primary(const SceneDev& sc, const JobParams& job, int, int traversal, int* d_id, float* d_t,
@@ -1668,6 +1683,17 @@ void wf_trace_shadow(const SceneDev& sc, const float* d_rays, int n, int travers
 void wf_rng_states(const JobParams& job, int frame_local, int first_pixel, int n, uint32_t* d_states,
                    cudaStream_t s) {
     k_rng_states<<<grid_for(n), kBlock, 0, s>>>(job, frame_local, first_pixel, n, d_states);
+}
+
+// 128-byte wide nodes -> compressed 64-byte nodes; *d_bad counts nodes whose boxes could not be contained (never
+// seen; the caller then keeps the uncompressed nodes)
+void wf_compress_nodes(const float4* d_wide, int n, uint4* d_cnodes, int* d_bad, cudaStream_t s) {
+    if (n > 0) k_compress_nodes<<<grid_for(n), kBlock, 0, s>>>(d_wide, n, reinterpret_cast<CNode*>(d_cnodes), d_bad);
+}
+
+void wf_instance_objects(const float4* d_unit, int n_unit, const float4* d_inst, int n_inst, float4* d_out, cudaStream_t s) {
+    const long long total = (long long)n_unit * n_inst * 7;
+    k_instance_objects<<<(unsigned)((total + kBlock - 1) / kBlock), kBlock, 0, s>>>(d_unit, n_unit, d_inst, n_inst, d_out);
 }
 
 void wf_tonemap(const float* d_accum, int n_pixels, int frames, uint32_t* d_argb, cudaStream_t s) {
