@@ -7,7 +7,7 @@ CSRC      := tryraytrace_b200/csrc
 LIBDIR    := tryraytrace_b200/lib
 OBJDIR    := build/obj
 INC       := -Iinclude -I$(CSRC) -I$(CSRC)/kernels -I/usr/local/cuda/include
-NVCCFLAGS := -O3 $(ARCH) --use_fast_math -lineinfo -std=c++17 $(INC) -Xcompiler -fPIC,-fopenmp
+NVCCFLAGS := -O3 $(ARCH) --use_fast_math -lineinfo -std=c++17 $(INC) -Xcompiler -fPIC,-fopenmp $(NVCCFLAGS_EXTRA)
 CXXFLAGS  := -O3 -march=x86-64-v3 -fopenmp -fPIC -std=c++17 $(INC) -Wall -Wno-unknown-pragmas
 
 HOST_SRC  := loader bvh scene camera image_io pipeline renderer xorwow_tables wide_bvh
@@ -43,7 +43,7 @@ $(OBJDIR)/trt_capi.o: $(CSRC)/capi/trt_capi.cu $(wildcard $(CSRC)/kernels/*.cuh)
 
 $(LIBDIR)/libtrt_b200.so: $(HOST_OBJS) $(CU_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -shared $(ARCH) -o $@ $^ -Xcompiler -fopenmp -Xlinker -Bsymbolic -lgomp
+	$(NVCC) -shared $(ARCH) -o $@ $^ -Xcompiler -fopenmp -Xlinker -Bsymbolic -lgomp -ldl
 
 # single-process multi-GPU layer (include/trt_mgpu.h): its own library, because it links NCCL
 $(LIBDIR)/libtrt_b200_mgpu.so: $(CSRC)/capi/trt_mgpu.cpp include/trt_mgpu.h include/trt_capi.h $(LIBDIR)/libtrt_b200.so

@@ -36,6 +36,15 @@ int trt_mgpu_upload_scene(trt_mgpu* m, const void* objects, int n_objects, const
 int trt_mgpu_render_to_host(trt_mgpu* m, float* h_accum, int width, int height, int first_frame_seed,
                             int n_frames, const void* cam, const trt_opts* opts, float* pass_ms);
 
+/* The same pass ADDED into a caller-owned device buffer on the first GPU of the set (w*h*16 bytes, running sum) --
+ * what n_frames calls of launch_render_kernel do to d_accum in the reference's main loop (src/main.cpp:181), spread
+ * over the GPUs.  GPU 0 renders its share of the frames straight into d_accum, the others into zeroed buffers of their
+ * own, and ONE ncclReduce to GPU 0 (in place on d_accum) sums them: d_accum += all n_frames samples.  This is the
+ * entry the drop-in renderer boundary (include/renderer.h launch_render_frames) uses when TRT_GPUS > 1.  d_accum
+ * must have been allocated on that first GPU; work already queued on its legacy default stream is waited for. */
+int trt_mgpu_render_accumulate(trt_mgpu* m, float* d_accum, int width, int height, int first_frame_seed,
+                               int n_frames, const void* cam, const trt_opts* opts, float* pass_ms);
+
 /* closest-hit + shadow queries of the last pass, summed over the GPUs */
 int trt_mgpu_rays(trt_mgpu* m, uint64_t* closest, uint64_t* shadow);
 

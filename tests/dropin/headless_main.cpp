@@ -7,6 +7,7 @@
 // All CUDA calls here are on the legacy default stream, exactly like the reference's.
 // usage: headless_main <asset_dir> <config> <width> <height> <frames> <out_prefix> [noaccum]
 // noaccum: the caller does not read h_accum (pipeline_set_host_accum(false)): 4 bytes per pixel per displayed frame
+// batch:   all frames in ONE launch_render_frames call (the batched entry; with TRT_GPUS=N it is split over N GPUs)
 #include "bvh.h"
 #include "camera.h"
 #include "pipeline.h"
@@ -52,8 +53,14 @@ int main(int argc, char** argv) {
     const bool no_accum = argc > 7 && std::string(argv[7]) == "noaccum";
     if (no_accum) pipeline_set_host_accum(&pipe, false);
 
+    const bool batch = argc > 7 && std::string(argv[7]) == "batch";
     int shown = 0;
-    for (int gpu_frame = 1; gpu_frame <= frames; gpu_frame++) {  // main.cpp:152-223
+    if (batch) {
+        launch_render_frames(d_accum, width, height, 1, frames, cam.get_params(width, height));
+        cudaMemcpy(d_staging, d_accum, n * sizeof(Vec), cudaMemcpyDeviceToDevice);
+        cudaDeviceSynchronize();
+    }
+    for (int gpu_frame = 1; gpu_frame <= frames && !batch; gpu_frame++) {  // main.cpp:152-223
         CameraParams cp = cam.get_params(width, height);
         launch_render_kernel(d_accum, width, height, gpu_frame, 16, 16, cp);          // :181
         cudaMemcpy(d_staging, d_accum, n * sizeof(Vec), cudaMemcpyDeviceToDevice);   // :188

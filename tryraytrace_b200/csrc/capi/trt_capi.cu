@@ -309,6 +309,10 @@ LaunchDims launch_dims(const trt_ctx* c) {
     if (const char* e = getenv("TRT_RANKED_TOP")) ranked = atoi(e) != 0;
     d.closest_phases = Phases{2, 12, 8, ranked};
     d.shadow_phases = Phases{2, 12, 8, 0};
+    if (d.wide_loads) {  // deep trees (C5: 40 node steps per ray, 5 lanes per triangle step): longer node phases, -6 %
+        d.closest_phases = Phases{4, 12, 8, ranked};
+        d.shadow_phases = Phases{4, 12, 8, 0};
+    }
     if (const char* e = getenv("TRT_PHASES")) {  // "iters,node_min,tri_min[,iters,node_min,tri_min]" closest[,shadow]
         int v[6] = {1, 33, 33, 1, 33, 33};
         const int n = sscanf(e, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);

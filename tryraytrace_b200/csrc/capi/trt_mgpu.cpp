@@ -142,6 +142,59 @@ int trt_mgpu_render_to_host(trt_mgpu* m, float* h_accum, int width, int height, 
     return 0;
 }
 
+int trt_mgpu_render_accumulate(trt_mgpu* m, float* d_accum, int width, int height, int first_frame_seed, int n_frames,
+                               const void* cam, const trt_opts* opts, float* pass_ms) {
+    if (!m || !d_accum || !cam || width <= 0 || height <= 0 || n_frames < 0) return TRT_ERR_ARG;
+    const int G = (int)m->ctx.size();
+    const size_t bytes = (size_t)width * height * 16;
+    if (bytes != m->accum_bytes) {
+        m->accum_bytes = 0;
+        for (int g = 0; g < G; g++) {
+            MCU(cudaSetDevice(m->devices[g]));
+            cudaFree(m->accum[g]);
+            m->accum[g] = nullptr;
+            MCU(cudaMalloc(&m->accum[g], bytes));
+        }
+        m->accum_bytes = bytes;
+    }
+    MCU(cudaSetDevice(m->devices[0]));
+    MCU(cudaStreamSynchronize(cudaStreamLegacy));  // the caller's cudaMemset / snapshot copies of d_accum
+    const auto t0 = std::chrono::steady_clock::now();
+    const int active = n_frames < G ? (n_frames > 0 ? n_frames : 1) : G;  // GPUs that have a frame to render
+    std::vector<int> rc(G, 0);
+    std::vector<std::string> err(G);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; g++) {
+        workers.emplace_back([&, g]() {
+            cudaSetDevice(m->devices[g]);
+            trt_reset_counters(m->ctx[g]);
+            float* target = g == 0 ? d_accum : m->accum[g];
+            if (g != 0 && active > 1) cudaMemsetAsync(target, 0, bytes, m->streams[g]);
+            const int mine = n_frames > g ? (n_frames - g + G - 1) / G : 0;
+            if (mine > 0) rc[g] = trt_render(m->ctx[g], target, width, height, first_frame_seed + g, mine, G, cam, opts);
+            if (rc[g]) err[g] = trt_last_error();
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int g = 0; g < G; g++)
+        if (rc[g]) return mfail("trt_render", err[g].c_str()), rc[g];
+    if (active > 1) {  // one reduction per pass, to the GPU that owns the caller's buffer (in place there)
+        MNCCL(ncclGroupStart());
+        for (int g = 0; g < G; g++) {
+            float* buf = g == 0 ? d_accum : m->accum[g];
+            MNCCL(ncclReduce(buf, buf, (size_t)width * height * 4, ncclFloat, ncclSum, 0, m->comms[g], m->streams[g]));
+        }
+        MNCCL(ncclGroupEnd());
+    }
+    for (int g = 0; g < G; g++) {
+        MCU(cudaSetDevice(m->devices[g]));
+        MCU(cudaStreamSynchronize(m->streams[g]));
+    }
+    MCU(cudaSetDevice(m->devices[0]));
+    if (pass_ms) *pass_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
 int trt_mgpu_rays(trt_mgpu* m, uint64_t* closest, uint64_t* shadow) {
     if (!m) return TRT_ERR_ARG;
     uint64_t c = 0, s = 0;

@@ -4,12 +4,62 @@
 #include "renderer.h"
 #include "image_io.h"
 #include "trt_capi.h"
+#include "trt_mgpu.h"
 #include <cuda_runtime_api.h>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 namespace {
 trt_ctx* g_ctx = nullptr;
+
+// North-star subsystem (3) behind the reference's own entry points: with TRT_GPUS=N (N > 1) the scene is replicated
+// on N GPUs and launch_render_frames splits its frames over them by sample index, one ncclReduce per call into the
+// caller's buffer (include/trt_mgpu.h).  The layer lives in libtrt_b200_mgpu.so (it links NCCL), which sits next to
+// this library and is opened on first use; without TRT_GPUS nothing of it is touched.
+struct MgpuApi {
+    void* lib = nullptr;
+    trt_mgpu* m = nullptr;
+    int (*create)(int, const int*, trt_mgpu**) = nullptr;
+    int (*upload)(trt_mgpu*, const void*, int, const void*, int, const int*, int, const trt_image*, int) = nullptr;
+    int (*render_accumulate)(trt_mgpu*, float*, int, int, int, int, const void*, const trt_opts*, float*) = nullptr;
+    bool tried = false;
+} g_mgpu;
+
+int wanted_gpus() {
+    const char* e = std::getenv("TRT_GPUS");
+    return e ? std::atoi(e) : 1;
+}
+
+trt_mgpu* global_mgpu() {
+    if (g_mgpu.tried) return g_mgpu.m;
+    g_mgpu.tried = true;
+    const int n = wanted_gpus();
+    if (n < 1 || (n == 1 && !std::getenv("TRT_MGPU_FORCE"))) return nullptr;  // TRT_MGPU_FORCE: the layer on one GPU (tests)
+    Dl_info info;
+    std::string path = "libtrt_b200_mgpu.so";
+    if (dladdr((const void*)&wanted_gpus, &info) && info.dli_fname) {
+        const std::string self = info.dli_fname;
+        const size_t slash = self.rfind('/');
+        if (slash != std::string::npos) path = self.substr(0, slash + 1) + path;
+    }
+    g_mgpu.lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!g_mgpu.lib) {
+        std::fprintf(stderr, "[Renderer Error] TRT_GPUS=%d but %s cannot be loaded: %s\n", n, path.c_str(), dlerror());
+        return nullptr;
+    }
+    g_mgpu.create = (decltype(g_mgpu.create))dlsym(g_mgpu.lib, "trt_mgpu_create");
+    g_mgpu.upload = (decltype(g_mgpu.upload))dlsym(g_mgpu.lib, "trt_mgpu_upload_scene");
+    g_mgpu.render_accumulate = (decltype(g_mgpu.render_accumulate))dlsym(g_mgpu.lib, "trt_mgpu_render_accumulate");
+    if (!g_mgpu.create || !g_mgpu.upload || !g_mgpu.render_accumulate || g_mgpu.create(n, nullptr, &g_mgpu.m) != 0) {
+        std::fprintf(stderr, "[Renderer Error] multi-GPU layer unavailable (TRT_GPUS=%d)\n", n);
+        g_mgpu.m = nullptr;
+    } else {
+        std::printf("[Renderer] %d GPUs: frames of launch_render_frames are split by sample index, one reduction per call.\n", n);
+    }
+    return g_mgpu.m;
+}
 
 trt_ctx* global_ctx() {
     if (!g_ctx) {
@@ -31,8 +81,9 @@ trt_ctx* global_ctx() {
 
 void init_scene_data(const std::vector<Object>& objects, const std::vector<std::string>& texture_files,
                      const std::vector<LinearBVHNode>& nodes, const std::vector<int>& light_indices) {
-    trt_ctx* c = global_ctx();
-    if (!c) return;
+    trt_mgpu* mg = global_mgpu();
+    trt_ctx* c = mg ? nullptr : global_ctx();
+    if (!c && !mg) return;
     // Texture slot i belongs to texture_files[i] (objects name it by tex_id).  A file that fails to load keeps
     // its slot -- the reference stores a null handle there (src/renderer.cu:97-126) -- so later indices do not
     // shift: the slot gets a 1x1 placeholder and exactly the objects that named it fall back to untextured.
@@ -54,8 +105,11 @@ void init_scene_data(const std::vector<Object>& objects, const std::vector<std::
     std::vector<Object> objs = objects;
     for (Object& o : objs)
         if (o.tex_id >= (int)imgs.size() || (o.tex_id >= 0 && failed[o.tex_id])) o.tex_id = -1;
-    if (trt_upload_scene(c, objs.data(), (int)objs.size(), nodes.data(), (int)nodes.size(), light_indices.data(),
-                         (int)light_indices.size(), imgs.data(), (int)imgs.size()) != 0)
+    const int rc = mg ? g_mgpu.upload(mg, objs.data(), (int)objs.size(), nodes.data(), (int)nodes.size(), light_indices.data(),
+                                      (int)light_indices.size(), imgs.data(), (int)imgs.size())
+                      : trt_upload_scene(c, objs.data(), (int)objs.size(), nodes.data(), (int)nodes.size(), light_indices.data(),
+                                         (int)light_indices.size(), imgs.data(), (int)imgs.size());
+    if (rc != 0)
         std::fprintf(stderr, "[Renderer Error] %s\n", trt_last_error());
     else
         std::printf("[Renderer] Uploaded %zu objects, %zu BVH nodes, %zu lights.\n", objects.size(), nodes.size(),
@@ -65,6 +119,12 @@ void init_scene_data(const std::vector<Object>& objects, const std::vector<std::
 
 void launch_render_frames(Vec* accum_buffer, int width, int height, int first_frame_seed, int n_frames,
                           CameraParams cam) {
+    if (trt_mgpu* mg = global_mgpu()) {  // TRT_GPUS > 1: synchronous (the reduction ends the call)
+        if (g_mgpu.render_accumulate(mg, reinterpret_cast<float*>(accum_buffer), width, height, first_frame_seed, n_frames, &cam,
+                                     nullptr, nullptr) != 0)
+            std::fprintf(stderr, "[Renderer Error] multi-GPU pass failed\n");
+        return;
+    }
     trt_ctx* c = global_ctx();
     if (!c) return;
     if (trt_render(c, reinterpret_cast<float*>(accum_buffer), width, height, first_frame_seed, n_frames, 1, &cam,

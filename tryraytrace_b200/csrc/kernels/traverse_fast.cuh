@@ -386,6 +386,10 @@ TRT_DEV float4 cnode_planes(uint32_t q_word, float scale, float base) {
     return make_float4(cnode_plane(q_word, 0, scale, base), cnode_plane(q_word, 1, scale, base),
                        cnode_plane(q_word, 2, scale, base), cnode_plane(q_word, 3, scale, base));
 }
+// line of a compressed node into L1 ahead of the node step that will read it (no register, no wait)
+TRT_DEV void prefetch_cnode(const SceneDev& sc, int node, bool p) {
+    if (p) asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const unsigned char*>(sc.cnodes) + (size_t)node * 64));
+}
 TRT_DEV void ldg256u(const unsigned char* p, uint4& a, uint4& b) {
     asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
@@ -698,6 +702,9 @@ TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const S
     const int r01 = (best & 1u) ? r[1] : r[0], r23 = (best & 1u) ? r[3] : r[2];
     const int rb = (best & 2u) ? r23 : r01;
     s.cur = best != 0xffffffffu ? rb : kWideEmptyRef;
+    // big scenes: the node this lane opens next is known now -- start its line on the way to L1 (the step that reads it
+    // comes after the other lanes' work of this round; the kernel waits on node fetches more than on anything else there)
+    if (WIDE) prefetch_cnode(sc, s.cur, best != 0xffffffffu);
 #pragma unroll
     for (int k = 0; k < 4; k++) push_child<E>(s.np, s.tp, tn[k], tf[k], r[k], key[k], best);
 }
@@ -876,6 +883,11 @@ TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const Sc
     push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.y, ay.y), fmaxf(az.y, lo)), fminf(fminf(bx.y, by.y), fminf(bz.y, hi)), n.ch.y);
     push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.z, ay.z), fmaxf(az.z, lo)), fminf(fminf(bx.z, by.z), fminf(bz.z, hi)), n.ch.z);
     push_child_any<E>(s.np, s.tp, fmaxf(fmaxf(ax.w, ay.w), fmaxf(az.w, lo)), fminf(fminf(bx.w, by.w), fminf(bz.w, hi)), n.ch.w);
+    if (WIDE) {  // the node the next step pops
+        const bool any = s.np != base;
+        const int nxt = any ? (int)lds32(s.np - E) : 0;
+        prefetch_cnode(sc, nxt, any);
+    }
 }
 
 // one triangle per step (the any-hit kernel keeps this form: the packed pair test needs eight more registers,

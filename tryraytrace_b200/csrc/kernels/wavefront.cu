@@ -21,9 +21,11 @@ constexpr int kCompactMinCap = 32 * 1024;  // the pool is not compacted below th
 
 TRT_DEV int pack_flags(int state, int depth, int mode) { return state | (depth << 8) | (mode << 16); }
 
-// A paired 32-byte record (PoolView::od, ::rs) in ONE 256-bit access (sm_100 LDG.E.256 / STG.E.256): a warp's 32
-// records are 1 KB contiguous, so the access is fully coalesced; two 128-bit accesses at a 32-byte stride would each
-// use half of every sector they touch.
+// A paired 32-byte record (PoolView::od, ::rs) is LOADED with one 256-bit access (sm_100 LDG.E.256): a warp's 32
+// records are 1 KB contiguous, so the load is fully coalesced, where two 128-bit loads at a 32-byte stride each use
+// half of every sector they touch (shade: -4 %).  Records are STORED as two 128-bit halves: the halves of a sector
+// written by one thread merge in L2; the 256-bit store form (st.global.v8) was measured equal (shade -0.8 %) and
+// is not used.
 TRT_DEV void ld_rec(const float4* rec, float4& a, float4& b) {
     asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
@@ -34,16 +36,8 @@ TRT_DEV void ld_rec(const uint4* rec, uint4& a, uint4& b) {
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
                  : "l"(rec));
 }
-TRT_DEV void st_rec(float4* rec, const float4 a, const float4 b) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rec), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
-                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
-                 : "memory");
-}
-TRT_DEV void st_rec(uint4* rec, const uint4 a, const uint4 b) {
-    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(rec), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
-                 "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                 : "memory");
-}
+TRT_DEV void st_rec(float4* rec, const float4 a, const float4 b) { rec[0] = a; rec[1] = b; }
+TRT_DEV void st_rec(uint4* rec, const uint4 a, const uint4 b) { rec[0] = a; rec[1] = b; }
 
 __global__ void k_begin_job(Control* ctl, unsigned long long total, int capacity) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -1494,6 +1488,7 @@ int opt_in_smem(K kernel) {
 // ---- launchers -------------------------------------------------------------------------------
 int wf_configure() {
     int rc = 0;
+
     rc |= opt_in_smem(k_extend_fast<512, false, false>);
     rc |= opt_in_smem(k_extend_fast<512, true, false>);
     rc |= opt_in_smem(k_extend_fast<768, false, false>);
