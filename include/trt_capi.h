@@ -149,9 +149,14 @@ int trt_scene_info_get(trt_ctx* ctx, trt_scene_info* out);
  * src/renderer.cu:764-770) with frame_seed = first_frame_seed .. +n_frames-1:
  * adds one sample per pixel per frame into d_accum (DEVICE pointer, w*h records of
  * 16 bytes = struct Vec, running sum, caller-zeroed).  cam: 80-byte CameraParams
- * (include/scene.h:64-72).  Asynchronous on the context's stream; use
- * trt_synchronize.  Frames may be sharded: frame_stride > 1 renders
- * first, first+stride, ... (n_frames of them) -- the multi-GPU sample split. */
+ * (include/scene.h:64-72).  The work runs on the context's stream.  Unlike the reference's
+ * launch (src/renderer.cu:764-770, one kernel, returns at once) the call follows the job on the
+ * host: it issues the wavefront iterations in batches and polls the device's control block
+ * between them (grid sizes, compaction and the drain tail depend on it), so it returns when
+ * the job has drained on the device up to the batches still queued behind the last live
+ * path -- call trt_synchronize before reading d_accum from another stream.  Frames may be
+ * sharded: frame_stride > 1 renders first, first+stride, ... (n_frames of them) -- the
+ * multi-GPU sample split. */
 int trt_render(trt_ctx* ctx, float* d_accum, int width, int height,
                int first_frame_seed, int n_frames, int frame_stride,
                const void* cam, const trt_opts* opts);
