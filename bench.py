@@ -434,7 +434,7 @@ def main():
     rays, samples, launches = float(t[1]), float(t[2]), int(t[3])
     value = rays / (ms * 1e-3) / 1e6
 
-    # per-kernel split of one more step (all marks on; regenerate overlaps the shadow kernel)
+    # per-kernel split of one more step (all marks on)
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev2.record(stream)
     step(1 + (args.warmup + args.steps) * args.spp * world, split_opts)

@@ -291,6 +291,7 @@ LaunchDims launch_dims(const trt_ctx* c) {
     // trees beyond a few MB: the node fetch is bound by L1 requests; the upload has compressed the nodes to 64 bytes
     // (two 256-bit loads per node step) and the kernels read that form, nothing staged
     d.wide_loads = c->sc.cnodes != nullptr;
+    if (d.wide_loads) d.fast_threads = 768;  // the compressed-node kernels exist for 768-thread CTAs only
     d.refill_below = 32;
     d.shade_block = 128;
     d.shade_minb = 8;
@@ -435,18 +436,18 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
     if (int rc = ensure_rng_tables(c, w, h)) return rc;
     int kFrameChunk = kFrameChunkDefault;
     if (const char* e = getenv("TRT_FRAME_CHUNK")) kFrameChunk = std::max(1, std::min(1024, atoi(e)));
-    // pool_paths = 0: size the pool to the job -- a quarter of the samples of one job (at most
-    // kFrameChunk frames) in flight, between 256 Ki and 32 Mi slots.  B200 sweeps with drain compaction,
-    // overlapped regeneration and poll-driven grids: every iteration has a fixed cost (launch gaps, the
-    // start-up and tail of the persistent kernels), so fewer, larger iterations win until the drain phase
-    // dominates -- C1 (4.9 M samples) 0.53 / 0.46 / 0.42 ms/spp at 512 Ki / 1 Mi / 2 Mi, C2 at 64 spp
-    // (133 M samples) 3.01 / 2.82 / 2.73 / 2.72 at 4 / 8 / 16 / 32 Mi, C4 9.96 / 9.81 at 16 / 32 Mi
+    // pool_paths = 0: size the pool to the job -- the largest power of two that the samples of one job (at most
+    // kFrameChunk frames) fill, between 256 Ki and 32 Mi slots.  Every iteration has a fixed cost (launch gaps, the
+    // start-up and tail of the persistent kernel), so fewer, larger iterations win: a job that fits the pool is one
+    // refill and a drain.  B200, C2: 1 spp (2.1 M samples) 8.34 / 6.06 / 4.93 / 4.51 / 4.72 ms at 256 Ki / 512 Ki /
+    // 1 Mi / 2 Mi / 4 Mi; 4 spp 3.41 / 3.19 / 3.07 ms/spp at 2 / 4 / 8 Mi; 16 spp 2.71 / 2.64 / 2.65 at 8 / 16 / 32 Mi;
+    // 64 spp (133 M samples) 2.59 / 2.50 / 2.47 at 8 / 16 / 32 Mi; C1 (4.9 M samples) 0.331 / 0.302 / 0.299 / 0.309 at
+    // 1 / 2 / 4 / 8 Mi
     int pool_paths = o.pool_paths;
     if (pool_paths == 0) {
-        const unsigned long long want =
-            (unsigned long long)w * h * (unsigned long long)std::min(n_frames, kFrameChunk) / 4;
+        const unsigned long long job = (unsigned long long)w * h * (unsigned long long)std::min(n_frames, kFrameChunk);
         pool_paths = 256 << 10;
-        while (pool_paths < (32 << 20) && (unsigned long long)pool_paths < want) pool_paths <<= 1;
+        while (pool_paths < (32 << 20) && 2ull * (unsigned long long)pool_paths * 100 <= job * 105) pool_paths <<= 1;
     }
     if (int rc = ensure_pool(c, pool_paths)) return rc;
     if (int rc = ensure_col_vecs(c, (size_t)std::min(n_frames, kFrameChunk) * w)) return rc;

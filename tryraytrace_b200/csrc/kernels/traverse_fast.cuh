@@ -890,8 +890,8 @@ TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const Sc
     }
 }
 
-// one triangle per step (the any-hit kernel keeps this form: the packed pair test needs eight more registers,
-// which takes the room the overlapped regenerate CTAs live in)
+// one triangle per step (the any-hit work keeps this form: the packed pair test costs registers and a spill in the
+// combined kernel and a shadow leaf visit usually ends at its first hit -- measured 98.5 -> 106.7 ms per 64 spp)
 template <uint32_t E, int S, bool COUNT>
 TRT_DEV void shadow_tri_step(const SceneDev& sc, ShadowRay& s, uint32_t base, WideCounts* wc) {
     const uint32_t ttop = base + (S - 1) * E;

@@ -195,7 +195,7 @@ TRT_DEV Xorwow sample_rng(const JobParams& job, int f, int row, int col) {
 //      a plane fall into 16 different banks, so the 200 look-ups of a sample are conflict-free LDS.32 instead
 //      of 80 scattered global loads; lanes whose row is not staged (images narrower than a batch) use the
 //      global table,
-//   4. the block that finishes last does what the single-thread k_prepare used to do: clamps next_sample,
+//   4. the block that finishes last closes the iteration's bookkeeping (a single-thread kernel in round 1): clamps next_sample,
 //      counts the samples, resets the traversal cursor and decides about a drain-phase compaction.
 // Which sample lands in which slot depends on the order the blocks reserve their ranges; the image does not
 // (a sample's RNG stream is a function of its frame and pixel alone).
