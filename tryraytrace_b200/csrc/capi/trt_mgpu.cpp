@@ -33,6 +33,13 @@ int mfail(const char* what, const char* detail) {
         cudaError_t e_ = (call);                                               \
         if (e_ != cudaSuccess) return mfail(#call, cudaGetErrorString(e_));    \
     } while (0)
+// every entry point leaves the calling thread's current device as it found it (the reference application never
+// changes it; the drop-in boundary allocates its buffers on it after init_scene_data has returned)
+struct DeviceGuard {
+    int prev = 0;
+    DeviceGuard() { cudaGetDevice(&prev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
 #define MNCCL(call)                                                            \
     do {                                                                       \
         ncclResult_t r_ = (call);                                              \
@@ -44,6 +51,7 @@ extern "C" {
 
 int trt_mgpu_create(int n_gpus, const int* devices, trt_mgpu** out) {
     if (!out || n_gpus < 1) return TRT_ERR_ARG;
+    DeviceGuard guard;
     int have = 0;
     if (cudaGetDeviceCount(&have) != cudaSuccess || have < n_gpus) return mfail("trt_mgpu_create", "not enough CUDA devices");
     trt_mgpu* m = new trt_mgpu();
@@ -72,6 +80,7 @@ int trt_mgpu_create(int n_gpus, const int* devices, trt_mgpu** out) {
 
 int trt_mgpu_destroy(trt_mgpu* m) {
     if (!m) return 0;
+    DeviceGuard guard;
     for (size_t g = 0; g < m->ctx.size(); g++) {
         cudaSetDevice(m->devices[g]);
         if (m->comms[g]) ncclCommDestroy(m->comms[g]);
@@ -87,6 +96,7 @@ int trt_mgpu_count(const trt_mgpu* m) { return m ? (int)m->ctx.size() : 0; }
 int trt_mgpu_upload_scene(trt_mgpu* m, const void* objects, int n_objects, const void* nodes, int n_nodes,
                           const int* lights, int n_lights, const trt_image* textures, int n_textures) {
     if (!m) return TRT_ERR_ARG;
+    DeviceGuard guard;
     for (size_t g = 0; g < m->ctx.size(); g++)
         if (int rc = trt_upload_scene(m->ctx[g], objects, n_objects, nodes, n_nodes, lights, n_lights, textures, n_textures))
             return mfail("trt_upload_scene", trt_last_error()), rc;
@@ -96,6 +106,7 @@ int trt_mgpu_upload_scene(trt_mgpu* m, const void* objects, int n_objects, const
 int trt_mgpu_render_to_host(trt_mgpu* m, float* h_accum, int width, int height, int first_frame_seed, int n_frames,
                             const void* cam, const trt_opts* opts, float* pass_ms) {
     if (!m || !h_accum || !cam || width <= 0 || height <= 0 || n_frames < 0) return TRT_ERR_ARG;
+    DeviceGuard guard;
     const int G = (int)m->ctx.size();
     const size_t bytes = (size_t)width * height * 16;
     if (bytes != m->accum_bytes) {
@@ -145,6 +156,7 @@ int trt_mgpu_render_to_host(trt_mgpu* m, float* h_accum, int width, int height, 
 int trt_mgpu_render_accumulate(trt_mgpu* m, float* d_accum, int width, int height, int first_frame_seed, int n_frames,
                                const void* cam, const trt_opts* opts, float* pass_ms) {
     if (!m || !d_accum || !cam || width <= 0 || height <= 0 || n_frames < 0) return TRT_ERR_ARG;
+    DeviceGuard guard;
     const int G = (int)m->ctx.size();
     const size_t bytes = (size_t)width * height * 16;
     if (bytes != m->accum_bytes) {
@@ -197,6 +209,7 @@ int trt_mgpu_render_accumulate(trt_mgpu* m, float* d_accum, int width, int heigh
 
 int trt_mgpu_rays(trt_mgpu* m, uint64_t* closest, uint64_t* shadow) {
     if (!m) return TRT_ERR_ARG;
+    DeviceGuard guard;
     uint64_t c = 0, s = 0;
     for (size_t g = 0; g < m->ctx.size(); g++) {
         trt_counters k;
