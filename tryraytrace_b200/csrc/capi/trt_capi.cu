@@ -297,8 +297,6 @@ LaunchDims launch_dims(const trt_ctx* c) {
     d.shade_minb = 8;
     if (const char* e = getenv("TRT_SHADE_MINB")) d.shade_minb = atoi(e);
     if (const char* e = getenv("TRT_SHADE_BLOCK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512) d.shade_block = v; }
-    d.pdl = true;
-    if (const char* e = getenv("TRT_PDL")) d.pdl = atoi(e) != 0;
     d.merged_trace = true;
     if (const char* e = getenv("TRT_MERGED_TRACE")) d.merged_trace = atoi(e) != 0;
     d.finish_below = 128 << 10;

@@ -21,30 +21,6 @@ constexpr int kCompactMinCap = 32 * 1024;  // the pool is not compacted below th
 
 TRT_DEV int pack_flags(int state, int depth, int mode) { return state | (depth << 8) | (mode << 16); }
 
-// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl may start while the kernel before it in
-// the stream is still running its last blocks; pdl_wait() blocks until that kernel has completed and its writes are
-// visible, pdl_trigger() lets the kernel AFTER this one start its own prologue.  Used for refill -> trace -> shade:
-// the traversal CTAs stage the tree top and set up their barriers on the SMs the refill's last blocks have left,
-// and shade blocks issue the loads that do not depend on the traversal on the SMs whose traversal CTA has finished.
-// Without a programmatic primary (an ordinary kernel, an event record in between) the launch is an ordinary one.
-TRT_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-TRT_DEV void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-template <class... KArgs, class... Args>
-void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 // A paired 32-byte record (PoolView::od, ::rs) is LOADED with one 256-bit access (sm_100 LDG.E.256): a warp's 32
 // records are 1 KB contiguous, so the load is fully coalesced, where two 128-bit loads at a 32-byte stride each use
 // half of every sector they touch (shade: -4 %).  Records are STORED as two 128-bit halves: the halves of a sector
@@ -251,7 +227,6 @@ __global__ void __launch_bounds__(kRefillBlock, 4) k_refill(PoolView pool, Contr
     __shared__ int s_warp[kRefillBlock / 32];
     __shared__ int s_take;
     __shared__ unsigned long long s_base;
-    pdl_trigger();  // the traversal kernel behind this one may start its prologue (it waits for this grid before it reads the pool)
     const int cap = ctl->active_cap;
     const int n_words = (cap + 31) >> 5;
     const int w0 = blockIdx.x * kRefillBlock;
@@ -463,27 +438,19 @@ __global__ void __launch_bounds__(kBlock) k_extend_ref(PoolView pool, SceneDev s
 template <bool COUNT, bool FAST, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_shade(PoolView pool, Control* ctl, SceneDev sc, JobParams job, int eager) {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;  // capacity is a multiple of the block size
+    if (slot == 0) ctl->cursor_shadow = 0;                   // the shadow kernel of this iteration starts at chunk 0
     // The state loads go out BEFORE anything that depends on the control block has come back (the grid is
     // sized by the host's bound, every slot below it is valid memory): a dependent read of the control block
     // first cost every CTA an L2 round trip before its first state load.  `eager` is the host's knowledge
-    // (samples are still being handed out, the pool is mostly live).  What the traversal kernel does not write --
-    // ray, throughput, RNG / radiance record -- is requested before the wait for that kernel (programmatic dependent
-    // launch: this block may have started on an SM whose traversal CTA has already finished); the hit record and the
-    // pending contribution (an occluded shadow ray clears it) after it.
+    // (samples are still being handed out, the pool is mostly live).
     float4 o4, d4;
     ld_rec(pool.od + 2 * (size_t)slot, o4, d4);
     float4 thr4, pend4;
     float2 hit;
     uint4 ra, rb;
     if (eager) {
-        thr4 = pool.thr[slot];
-        ld_rec(pool.rs + 2 * (size_t)slot, ra, rb);
-    }
-    pdl_wait();
-    if (slot == 0) ctl->cursor_shadow = 0;                   // the next traversal's any-hit phase starts at chunk 0
-    if (eager) {
-        pend4 = pool.pend[slot];
-        hit = pool.hit[slot];
+        thr4 = pool.thr[slot]; pend4 = pool.pend[slot];
+        hit = pool.hit[slot]; ld_rec(pool.rs + 2 * (size_t)slot, ra, rb);
     }
     const int cap = ctl->active_cap;                         // a multiple of the block size
     if (blockIdx.x * blockDim.x >= cap) return;              // whole block beyond the visited prefix
@@ -1004,7 +971,7 @@ k_trace_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, C
     unsigned char* s_queue = reinterpret_cast<unsigned char*>(s_bars + WARPS * 4);
     float4* s_top = reinterpret_cast<float4*>(s_queue + WARPS * kQueueBytesClosest);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    // prologue: scene data only, so it may run while the kernel before this one (refill / compaction) is finishing
+    if (ctl->active_cap <= 0) return;  // the job's last paths were finished by k_finish_paths: nothing to visit
     stage_nodes<THREADS>(s_nodes, sc, k_smem);
     if (threadIdx.x < kMaxTop) {
         s_top[threadIdx.x * 3] = top.v0[threadIdx.x];
@@ -1017,9 +984,6 @@ k_trace_fast(PoolView pool, SceneDev sc, const __grid_constant__ TopPrims top, C
     }
     mbar_fence_init();
     __syncthreads();
-    pdl_wait();     // the pool and the control block are final from here on
-    pdl_trigger();  // shade blocks may take the SMs whose traversal CTA has finished (they wait for this grid before they read its results)
-    if (ctl->active_cap <= 0) return;  // the job's last paths were finished by k_finish_paths: nothing to visit
     const uint32_t stk_base = smem_addr(s_stack + threadIdx.x);
     float4* stage = s_stage + warp * (kStageBytesPerWarp / 16);
     unsigned char* queue = s_queue + warp * kQueueBytesClosest;
@@ -1450,15 +1414,15 @@ template <int THREADS, bool COUNT>
 void launch_trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                        const LaunchDims& dims, cudaStream_t s) {
     if (dims.wide_loads && THREADS == 768) {
-        launch_pdl(k_trace_fast<768, COUNT, true, false>, dim3(dims.sms), dim3(768), trace_smem_bytes<768>(0), s, dims.pdl,
-                   pool, sc, top, ctl, 0, dims.refill_below, dims.closest_phases, dims.shadow_phases);
+        k_trace_fast<768, COUNT, true, false><<<dims.sms, 768, trace_smem_bytes<768>(0), s>>>(
+            pool, sc, top, ctl, 0, dims.refill_below, dims.closest_phases, dims.shadow_phases);
         return;
     }
     // the two extra mbarriers per warp come out of the staged nodes
     const int extra_nodes = (int)(((size_t)(THREADS / 32) * 16 + kSmemNodeStride - 1) / kSmemNodeStride);
     const int k = max(0, min(dims.smem_nodes - extra_nodes, sc.n_wide_nodes));
-    launch_pdl(k_trace_fast<THREADS, COUNT, false, false>, dim3(dims.sms), dim3(THREADS), trace_smem_bytes<THREADS>(k), s, dims.pdl,
-               pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, dims.shadow_phases);
+    k_trace_fast<THREADS, COUNT, false, false><<<dims.sms, THREADS, trace_smem_bytes<THREADS>(k), s>>>(
+        pool, sc, top, ctl, k, dims.refill_below, dims.closest_phases, dims.shadow_phases);
 }
 template <bool COUNT>
 void trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl, const LaunchDims& dims,
@@ -1627,16 +1591,15 @@ static int iteration_impl(const PoolView& pool, Control* ctl, const SceneDev& sc
     const int shade_blocks = (visit + dims.shade_block - 1) / dims.shade_block;
     constexpr bool F = MODE == TRT_TRAVERSE_FAST;
     const int eager = (st.samples_left || st.mostly_live) ? 1 : 0;
-    const bool pdl = dims.pdl;
     if (dims.shade_block == 128) {
         switch (dims.shade_minb) {
-        case 10: launch_pdl(k_shade<COUNT, F, 128, 10>, dim3(shade_blocks), dim3(128), 0, s, pdl, pool, ctl, sc, job, eager); break;
-        case 12: launch_pdl(k_shade<COUNT, F, 128, 12>, dim3(shade_blocks), dim3(128), 0, s, pdl, pool, ctl, sc, job, eager); break;
-        case 14: launch_pdl(k_shade<COUNT, F, 128, 14>, dim3(shade_blocks), dim3(128), 0, s, pdl, pool, ctl, sc, job, eager); break;
-        default: launch_pdl(k_shade<COUNT, F, 128, 8>, dim3(shade_blocks), dim3(128), 0, s, pdl, pool, ctl, sc, job, eager); break;
+        case 10: k_shade<COUNT, F, 128, 10><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
+        case 12: k_shade<COUNT, F, 128, 12><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
+        case 14: k_shade<COUNT, F, 128, 14><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
+        default: k_shade<COUNT, F, 128, 8><<<shade_blocks, 128, 0, s>>>(pool, ctl, sc, job, eager); break;
         }
     } else {
-        launch_pdl(k_shade<COUNT, F, kShadeMaxBlock, 2>, dim3(shade_blocks), dim3(dims.shade_block), 0, s, pdl, pool, ctl, sc, job, eager);
+        k_shade<COUNT, F, kShadeMaxBlock, 2><<<shade_blocks, dims.shade_block, 0, s>>>(pool, ctl, sc, job, eager);
     }
     launched += 2;
     mark(4);

@@ -98,7 +98,6 @@ struct LaunchDims {
     bool debug_checks;     // k_refill / k_compact_move verify the state of every slot they overwrite (Control::cnt_violations)
     int compact_quarters;  // drain phase: compact when live paths <= this many quarters of the visited slots (1..3)
     int finish_below;      // drain tail: paths alive at which k_finish_paths runs the rest of the job to completion (0 = never)
-    bool pdl;              // programmatic dependent launch of the traversal and shade kernels (prologues overlap the tail before)
     bool merged_trace;     // shadow rays of the previous shade pass + closest-hit rays in one persistent launch
     Phases closest_phases, shadow_phases;
 };
