@@ -283,7 +283,7 @@ LaunchDims launch_dims(const trt_ctx* c) {
     d.fast_threads = 768;
     if (const char* e = getenv("TRT_FAST_THREADS")) {
         const int v = atoi(e);
-        if (v == 512 || v == 768 || v == 1024) d.fast_threads = v;
+        if (v == 512 || v == 768 || v == 896 || v == 1024) d.fast_threads = v;
     }
     const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
     d.smem_nodes = fit;
@@ -294,7 +294,7 @@ LaunchDims launch_dims(const trt_ctx* c) {
     if (d.wide_loads) d.fast_threads = 768;  // the compressed-node kernels exist for 768-thread CTAs only
     d.refill_below = 32;
     d.shade_block = 128;
-    d.shade_minb = 8;
+    d.shade_minb = 9;  // 56 registers, 8 bytes spilled: 1152 threads per SM; shade waits on memory (48.8 -> 46.9 ms per 64 spp; 10 CTAs = 48 registers spill 108 bytes: 48.6)
     if (const char* e = getenv("TRT_SHADE_MINB")) d.shade_minb = atoi(e);
     if (const char* e = getenv("TRT_SHADE_BLOCK")) { const int v = atoi(e); if (v == 64 || v == 128 || v == 256 || v == 512) d.shade_block = v; }
     d.merged_trace = true;

@@ -94,7 +94,7 @@ struct LaunchDims {
     int refill_below;   // idle lanes are refilled when fewer than this many lanes hold a ray
     int shade_block;    // threads per shade CTA (64 .. 512; the pool capacity is a multiple of 512): larger CTAs, fewer
                         // free-list atomics and barriers waiting on them
-    int shade_minb;     // 128-thread shade CTAs: resident CTAs per SM the register allocation aims for (8, 10, 12, 14)
+    int shade_minb;     // 128-thread shade CTAs: resident CTAs per SM the register allocation aims for (8, 9, 10, 12, 14)
     bool debug_checks;     // k_refill / k_compact_move verify the state of every slot they overwrite (Control::cnt_violations)
     int compact_quarters;  // drain phase: compact when live paths <= this many quarters of the visited slots (1..3)
     int finish_below;      // drain tail: paths alive at which k_finish_paths runs the rest of the job to completion (0 = never)
