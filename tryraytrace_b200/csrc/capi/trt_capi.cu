@@ -283,7 +283,7 @@ LaunchDims launch_dims(const trt_ctx* c) {
     d.fast_threads = 768;
     if (const char* e = getenv("TRT_FAST_THREADS")) {
         const int v = atoi(e);
-        if (v == 512 || v == 768 || v == 896 || v == 1024) d.fast_threads = v;
+        if (v == 512 || v == 768 || v == 1024) d.fast_threads = v;
     }
     const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
     d.smem_nodes = fit;

@@ -578,7 +578,6 @@ constexpr int kQueueBytesShadow = kQueueCap * (16 + 16);
 template <int THREADS> struct FastCfg;
 template <> struct FastCfg<512>  { static constexpr int SC = 16, SS = 16; };
 template <> struct FastCfg<768>  { static constexpr int SC = 12, SS = 12; };
-template <> struct FastCfg<896>  { static constexpr int SC = 10, SS = 10; };
 template <> struct FastCfg<1024> { static constexpr int SC = 8,  SS = 10; };
 
 constexpr int kClaimChunks = 4;  // chunks a warp claims per atomic on the global cursor (one round trip per 128 slots)
@@ -1430,7 +1429,6 @@ void trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, C
                 cudaStream_t s) {
     switch (dims.fast_threads) {
     case 1024: launch_trace_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
-    case 896: launch_trace_fast<896, COUNT>(pool, sc, top, ctl, dims, s); break;
     case 768: launch_trace_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
     default: launch_trace_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
@@ -1466,7 +1464,6 @@ void extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, 
                  cudaStream_t s) {
     switch (dims.fast_threads) {
     case 1024: launch_extend_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
-    case 896: launch_extend_fast<896, COUNT>(pool, sc, top, ctl, dims, s); break;
     case 768: launch_extend_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
     default: launch_extend_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
@@ -1476,7 +1473,6 @@ void shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, 
                  cudaStream_t s) {
     switch (dims.fast_threads) {
     case 1024: launch_shadow_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
-    case 896: launch_shadow_fast<896, COUNT>(pool, sc, top, ctl, dims, s); break;
     case 768: launch_shadow_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
     default: launch_shadow_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
@@ -1497,12 +1493,6 @@ int wf_configure() {
     rc |= opt_in_smem(k_extend_fast<512, true, false>);
     rc |= opt_in_smem(k_extend_fast<768, false, false>);
     rc |= opt_in_smem(k_extend_fast<768, true, false>);
-    rc |= opt_in_smem(k_extend_fast<896, false, false>);
-    rc |= opt_in_smem(k_extend_fast<896, true, false>);
-    rc |= opt_in_smem(k_shadow_fast<896, false, false>);
-    rc |= opt_in_smem(k_shadow_fast<896, true, false>);
-    rc |= opt_in_smem(k_trace_fast<896, false, false, false>);
-    rc |= opt_in_smem(k_trace_fast<896, true, false, false>);
     rc |= opt_in_smem(k_extend_fast<1024, false, false>);
     rc |= opt_in_smem(k_extend_fast<1024, true, false>);
     rc |= opt_in_smem(k_shadow_fast<512, false, false>);
@@ -1530,7 +1520,6 @@ size_t wf_fast_smem_bytes(int threads, int smem_nodes, bool shadow) {
     switch (threads) {
     case 512: return fast_smem_bytes<512>(smem_nodes, shadow);
     case 768: return fast_smem_bytes<768>(smem_nodes, shadow);
-    case 896: return fast_smem_bytes<896>(smem_nodes, shadow);
     case 1024: return fast_smem_bytes<1024>(smem_nodes, shadow);
     default: return 0;
     }
