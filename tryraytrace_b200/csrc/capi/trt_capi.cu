@@ -280,10 +280,10 @@ int ensure_scratch(trt_ctx* c, int n) {
 LaunchDims launch_dims(const trt_ctx* c) {
     LaunchDims d;
     d.sms = c->sms;
-    d.fast_threads = 768;
+    d.fast_threads = 896;  // 28 warps per SM at 70 registers: the traversal is issue bound and wants warps (512 -> 768 -> 896 threads: 59.3 / 50.4 / 48.4 ms per 32 spp)
     if (const char* e = getenv("TRT_FAST_THREADS")) {
         const int v = atoi(e);
-        if (v == 512 || v == 768 || v == 1024) d.fast_threads = v;
+        if (v == 512 || v == 768 || v == 896 || v == 1024) d.fast_threads = v;
     }
     const int fit = wf_fast_max_smem_nodes(d.fast_threads, c->smem_limit);
     d.smem_nodes = fit;
@@ -291,7 +291,7 @@ LaunchDims launch_dims(const trt_ctx* c) {
     // trees beyond a few MB: the node fetch is bound by L1 requests; the upload has compressed the nodes to 64 bytes
     // (two 256-bit loads per node step) and the kernels read that form, nothing staged
     d.wide_loads = c->sc.cnodes != nullptr;
-    if (d.wide_loads) d.fast_threads = 768;  // the compressed-node kernels exist for 768-thread CTAs only
+    if (d.wide_loads) d.fast_threads = 896;  // the compressed-node kernels exist for 896-thread CTAs only
     d.refill_below = 32;
     d.shade_block = 128;
     d.shade_minb = 9;  // 56 registers, 8 bytes spilled: 1152 threads per SM; shade waits on memory (48.8 -> 46.9 ms per 64 spp; 10 CTAs = 48 registers spill 108 bytes: 48.6)

@@ -348,8 +348,10 @@ struct NodeData {
     int4 ch;
 };
 
-// `near_off` packs the byte offsets of the near-plane vectors inside the 128-byte node:
-// x: 0 or 16, y: 32 or 48, z: 64 or 80; the far plane is the other one of each pair (^16).
+// nxo / nyo / nzo are the byte offsets of the near-plane vectors inside the 128-byte node:
+// x: 0 or 16, y: 32 or 48, z: 64 or 80; the far plane is the other one of each pair (^16).  They are derived from
+// the sign of the reciprocal direction at every node step (three selects) rather than carried in three registers:
+// the traversal kernels are issue bound and want warps, and 70 registers allow 28 warps per SM where 77 allowed 24.
 // The first k_smem nodes are staged in shared memory 112 bytes apart (the 16-byte plane vector a
 // lane reads then falls into bank group (k - node) mod 8, so lanes reading the same k of
 // different nodes spread over the banks), the rest sit in global memory 128 bytes apart.  Both
@@ -446,7 +448,6 @@ struct ClosestRay {
     float d_min;
     int id;
     int cur;            // next inner node to open (held in a register), or kWideEmptyRef
-    int nxo, nyo, nzo;  // near-plane byte offsets (see load_node)
     uint32_t np, tp;    // shared-window addresses of the next free node / triangle entry
     int nspill;         // entries in the local overflow
 };  // `id` is the winner's object index | kTriNoDerive (as stored in its record), -1 = none
@@ -457,9 +458,6 @@ TRT_DEV void closest_begin(ClosestRay& s, const float4 o4, const float4 d4, floa
     s.o = f3(o4.x, o4.y, o4.z);
     s.d = f3(d4.x, d4.y, d4.z);
     s.inv = f3(ref_safe_inv(s.d.x), ref_safe_inv(s.d.y), ref_safe_inv(s.d.z));
-    s.nxo = s.inv.x < 0.f ? 16 : 0;
-    s.nyo = s.inv.y < 0.f ? 48 : 32;
-    s.nzo = s.inv.z < 0.f ? 80 : 64;
     s.d_min = d_min;
     s.id = id;
     s.np = base;
@@ -681,7 +679,7 @@ TRT_DEV void closest_node_step(const unsigned char* s_nodes, int k_smem, const S
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node<WIDE>(n, s_nodes, k_smem, sc, node, s.nxo, s.nyo, s.nzo);
+    load_node<WIDE>(n, s_nodes, k_smem, sc, node, s.inv.x < 0.f ? 16 : 0, s.inv.y < 0.f ? 48 : 32, s.inv.z < 0.f ? 80 : 64);
     // slab intervals of the four children, packed two per instruction
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
@@ -759,7 +757,6 @@ TRT_DEV bool closest_done(const ClosestRay& s, uint32_t base) {
 struct ShadowRay {
     F3 o, d, inv;
     float max_dist, t_hi;
-    int nxo, nyo, nzo;
     uint32_t np, tp;
     int nspill;
     bool occluded;
@@ -771,9 +768,6 @@ TRT_DEV void shadow_begin(ShadowRay& s, const float4 o4, const float4 d4, uint32
     s.o = f3(o4.x, o4.y, o4.z);
     s.d = f3(d4.x, d4.y, d4.z);
     s.inv = f3(p_rcp(s.d.x), p_rcp(s.d.y), p_rcp(s.d.z));  // raw reciprocal, reference :276
-    s.nxo = s.inv.x < 0.f ? 16 : 0;
-    s.nyo = s.inv.y < 0.f ? 48 : 32;
-    s.nzo = s.inv.z < 0.f ? 80 : 64;
     s.max_dist = o4.w;
     s.t_hi = p_sub(o4.w, 0.001f);
     s.occluded = false;
@@ -873,7 +867,7 @@ TRT_DEV void shadow_node_step(const unsigned char* s_nodes, int k_smem, const Sc
     if (node == kWideEmptyRef) return;
     if (COUNT) wc->nodes++;
     NodeData n;
-    load_node<WIDE>(n, s_nodes, k_smem, sc, node, s.nxo, s.nyo, s.nzo);
+    load_node<WIDE>(n, s_nodes, k_smem, sc, node, s.inv.x < 0.f ? 16 : 0, s.inv.y < 0.f ? 48 : 32, s.inv.z < 0.f ? 80 : 64);
     const float4 ax = plane_t(n.nx, s.o.x, s.inv.x), bx = plane_t(n.fx, s.o.x, s.inv.x);
     const float4 ay = plane_t(n.ny, s.o.y, s.inv.y), by = plane_t(n.fy, s.o.y, s.inv.y);
     const float4 az = plane_t(n.nz, s.o.z, s.inv.z), bz = plane_t(n.fz, s.o.z, s.inv.z);

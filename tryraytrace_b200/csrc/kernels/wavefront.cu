@@ -578,6 +578,7 @@ constexpr int kQueueBytesShadow = kQueueCap * (16 + 16);
 template <int THREADS> struct FastCfg;
 template <> struct FastCfg<512>  { static constexpr int SC = 16, SS = 16; };
 template <> struct FastCfg<768>  { static constexpr int SC = 12, SS = 12; };
+template <> struct FastCfg<896>  { static constexpr int SC = 11, SS = 11; };
 template <> struct FastCfg<1024> { static constexpr int SC = 8,  SS = 10; };
 
 constexpr int kClaimChunks = 4;  // chunks a warp claims per atomic on the global cursor (one round trip per 128 slots)
@@ -1413,8 +1414,8 @@ size_t trace_smem_bytes(int k_smem) {  // the combined kernel: closest-hit layou
 template <int THREADS, bool COUNT>
 void launch_trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                        const LaunchDims& dims, cudaStream_t s) {
-    if (dims.wide_loads && THREADS == 768) {
-        k_trace_fast<768, COUNT, true, false><<<dims.sms, 768, trace_smem_bytes<768>(0), s>>>(
+    if (dims.wide_loads && THREADS == 896) {
+        k_trace_fast<896, COUNT, true, false><<<dims.sms, 896, trace_smem_bytes<896>(0), s>>>(
             pool, sc, top, ctl, 0, dims.refill_below, dims.closest_phases, dims.shadow_phases);
         return;
     }
@@ -1429,6 +1430,7 @@ void trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, C
                 cudaStream_t s) {
     switch (dims.fast_threads) {
     case 1024: launch_trace_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
+    case 896: launch_trace_fast<896, COUNT>(pool, sc, top, ctl, dims, s); break;
     case 768: launch_trace_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
     default: launch_trace_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
@@ -1437,8 +1439,8 @@ void trace_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, C
 template <int THREADS, bool COUNT>
 void launch_extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                         const LaunchDims& dims, cudaStream_t s) {
-    if (dims.wide_loads && THREADS == 768) {  // big scenes: 256-bit node loads, nothing staged
-        k_extend_fast<768, COUNT, true><<<dims.sms, 768, fast_smem_bytes<768>(0, false), s>>>(
+    if (dims.wide_loads && THREADS == 896) {  // big scenes: compressed nodes, nothing staged
+        k_extend_fast<896, COUNT, true><<<dims.sms, 896, fast_smem_bytes<896>(0, false), s>>>(
             pool, sc, top, ctl, 0, dims.refill_below, dims.closest_phases);
         return;
     }
@@ -1449,8 +1451,8 @@ void launch_extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims
 template <int THREADS, bool COUNT>
 void launch_shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, Control* ctl,
                         const LaunchDims& dims, cudaStream_t s) {
-    if (dims.wide_loads && THREADS == 768) {
-        k_shadow_fast<768, COUNT, true><<<dims.sms, 768, fast_smem_bytes<768>(0, true), s>>>(
+    if (dims.wide_loads && THREADS == 896) {
+        k_shadow_fast<896, COUNT, true><<<dims.sms, 896, fast_smem_bytes<896>(0, true), s>>>(
             pool, sc, top, ctl, 0, dims.refill_below, dims.shadow_phases);
         return;
     }
@@ -1464,6 +1466,7 @@ void extend_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, 
                  cudaStream_t s) {
     switch (dims.fast_threads) {
     case 1024: launch_extend_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
+    case 896: launch_extend_fast<896, COUNT>(pool, sc, top, ctl, dims, s); break;
     case 768: launch_extend_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
     default: launch_extend_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
@@ -1473,6 +1476,7 @@ void shadow_fast(const PoolView& pool, const SceneDev& sc, const TopPrims& top, 
                  cudaStream_t s) {
     switch (dims.fast_threads) {
     case 1024: launch_shadow_fast<1024, COUNT>(pool, sc, top, ctl, dims, s); break;
+    case 896: launch_shadow_fast<896, COUNT>(pool, sc, top, ctl, dims, s); break;
     case 768: launch_shadow_fast<768, COUNT>(pool, sc, top, ctl, dims, s); break;
     default: launch_shadow_fast<512, COUNT>(pool, sc, top, ctl, dims, s); break;
     }
@@ -1493,6 +1497,12 @@ int wf_configure() {
     rc |= opt_in_smem(k_extend_fast<512, true, false>);
     rc |= opt_in_smem(k_extend_fast<768, false, false>);
     rc |= opt_in_smem(k_extend_fast<768, true, false>);
+    rc |= opt_in_smem(k_extend_fast<896, false, false>);
+    rc |= opt_in_smem(k_extend_fast<896, true, false>);
+    rc |= opt_in_smem(k_shadow_fast<896, false, false>);
+    rc |= opt_in_smem(k_shadow_fast<896, true, false>);
+    rc |= opt_in_smem(k_trace_fast<896, false, false, false>);
+    rc |= opt_in_smem(k_trace_fast<896, true, false, false>);
     rc |= opt_in_smem(k_extend_fast<1024, false, false>);
     rc |= opt_in_smem(k_extend_fast<1024, true, false>);
     rc |= opt_in_smem(k_shadow_fast<512, false, false>);
@@ -1501,18 +1511,18 @@ int wf_configure() {
     rc |= opt_in_smem(k_shadow_fast<768, true, false>);
     rc |= opt_in_smem(k_shadow_fast<1024, false, false>);
     rc |= opt_in_smem(k_shadow_fast<1024, true, false>);
-    rc |= opt_in_smem(k_extend_fast<768, false, true>);
-    rc |= opt_in_smem(k_extend_fast<768, true, true>);
-    rc |= opt_in_smem(k_shadow_fast<768, false, true>);
-    rc |= opt_in_smem(k_shadow_fast<768, true, true>);
+    rc |= opt_in_smem(k_extend_fast<896, false, true>);
+    rc |= opt_in_smem(k_extend_fast<896, true, true>);
+    rc |= opt_in_smem(k_shadow_fast<896, false, true>);
+    rc |= opt_in_smem(k_shadow_fast<896, true, true>);
     rc |= opt_in_smem(k_trace_fast<512, false, false, false>);
     rc |= opt_in_smem(k_trace_fast<512, true, false, false>);
     rc |= opt_in_smem(k_trace_fast<768, false, false, false>);
     rc |= opt_in_smem(k_trace_fast<768, true, false, false>);
     rc |= opt_in_smem(k_trace_fast<1024, false, false, false>);
     rc |= opt_in_smem(k_trace_fast<1024, true, false, false>);
-    rc |= opt_in_smem(k_trace_fast<768, false, true, false>);
-    rc |= opt_in_smem(k_trace_fast<768, true, true, false>);
+    rc |= opt_in_smem(k_trace_fast<896, false, true, false>);
+    rc |= opt_in_smem(k_trace_fast<896, true, true, false>);
     return rc;
 }
 
@@ -1520,6 +1530,7 @@ size_t wf_fast_smem_bytes(int threads, int smem_nodes, bool shadow) {
     switch (threads) {
     case 512: return fast_smem_bytes<512>(smem_nodes, shadow);
     case 768: return fast_smem_bytes<768>(smem_nodes, shadow);
+    case 896: return fast_smem_bytes<896>(smem_nodes, shadow);
     case 1024: return fast_smem_bytes<1024>(smem_nodes, shadow);
     default: return 0;
     }
