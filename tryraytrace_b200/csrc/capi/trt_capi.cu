@@ -529,6 +529,9 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
             // kernel ride along from well above its threshold (it decides on the device)
             st.finish_below = (!st.samples_left && (long long)hc.alive <= 16ll * dims.finish_below) ? dims.finish_below : 0;
             if (near_drain) batch = kTailBatchIterations;
+            // once the tail kernel rides along the job can end in any iteration: single-iteration batches, so that at
+            // most two empty iterations are queued behind it (45 us each; a 1-spp call is 4.4 ms)
+            if (st.finish_below > 0) batch = 1;
             b++;
             if (issued > max_iterations) {
                 cudaStreamSynchronize(c->stream);
