@@ -78,10 +78,11 @@ struct trt_ctx {
     trt_scene_info info{};
 
     // XORWOW tables
-    int rng_w = 0, rng_h = 0, n_col_bits = 0;
+    int rng_w = 0, rng_h = 0;
     uint32_t* d_row_a = nullptr;  // window tables of the row matrices (words 0-3 / word 4)
     uint32_t* d_row_b = nullptr;
-    uint32_t* d_col_pows = nullptr;
+    uint32_t* d_col_a = nullptr;  // two-level column window tables (host/xorwow_tables.h xorwow_build_col_levels): words 0-3 ...
+    uint32_t* d_col_b = nullptr;  // ... and word 4 of the entries
     XwColVec* d_col_vecs = nullptr;
     size_t col_vecs_cap = 0;
 
@@ -177,23 +178,17 @@ int make_texture(trt_ctx* c, const trt_image& img) {
     return 0;
 }
 
-void pack_matrix(const Gf2Mat& m, uint32_t* dst) {  // 160 columns x 8 words
-    for (int b = 0; b < 160; b++) {
-        for (int k = 0; k < 5; k++) dst[b * 8 + k] = m.col[b][k];
-        dst[b * 8 + 5] = dst[b * 8 + 6] = dst[b * 8 + 7] = 0;
-    }
-}
-
 int ensure_rng_tables(trt_ctx* c, int w, int h) {
     if (c->rng_w == w && c->rng_h == h) return 0;
     cudaFree(c->d_row_a);
     cudaFree(c->d_row_b);
-    cudaFree(c->d_col_pows);
-    c->d_row_a = c->d_row_b = c->d_col_pows = nullptr;
+    cudaFree(c->d_col_a);
+    cudaFree(c->d_col_b);
+    c->d_row_a = c->d_row_b = c->d_col_a = c->d_col_b = nullptr;
     c->rng_w = c->rng_h = 0;
-    std::vector<Gf2Mat> rows, cols;
+    std::vector<Gf2Mat> rows, col_lo, col_hi;
     xorwow_build_row_matrices(w, h, rows);
-    xorwow_build_col_powers(w, cols);
+    xorwow_build_col_levels(w, col_lo, col_hi);
     std::vector<uint32_t> ta((size_t)h * kXwWindowEntries * 4), tb((size_t)h * kXwWindowEntries);
 #pragma omp parallel for schedule(static)
     for (int r = 0; r < h; r++)
@@ -202,12 +197,16 @@ int ensure_rng_tables(trt_ctx* c, int w, int h) {
     CU(cudaMalloc(&c->d_row_b, tb.size() * 4));
     CU(cudaMemcpyAsync(c->d_row_a, ta.data(), ta.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_row_b, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    std::vector<uint32_t> pc(cols.size() * kXwMatWords);
-    for (size_t j = 0; j < cols.size(); j++) pack_matrix(cols[j], pc.data() + j * kXwMatWords);
-    CU(cudaMalloc(&c->d_col_pows, pc.size() * 4));
-    CU(cudaMemcpyAsync(c->d_col_pows, pc.data(), pc.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    const size_t n_col = col_lo.size() + col_hi.size();
+    std::vector<uint32_t> ca(n_col * kXwWindowEntries * 4), cb(n_col * kXwWindowEntries);
+    for (size_t t = 0; t < n_col; t++)
+        xorwow_window_table(t < col_lo.size() ? col_lo[t] : col_hi[t - col_lo.size()], ca.data() + t * kXwWindowEntries * 4,
+                            cb.data() + t * kXwWindowEntries);
+    CU(cudaMalloc(&c->d_col_a, ca.size() * 4));
+    CU(cudaMalloc(&c->d_col_b, cb.size() * 4));
+    CU(cudaMemcpyAsync(c->d_col_a, ca.data(), ca.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_col_b, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->n_col_bits = (int)cols.size();
     c->rng_w = w;
     c->rng_h = h;
     return 0;
@@ -466,7 +465,7 @@ int render_impl(trt_ctx* c, float* d_accum, int w, int h, int first, int n_frame
         const int nf = std::min(kFrameChunk, n_frames - f0);
         JobParams job;
         fill_job(c, job, d_accum, w, h, first + f0 * stride, nf, stride, cam, o);
-        wf_col_table(c->d_col_pows, c->n_col_bits, w, job.first_frame_seed, stride, o.seed_base, nf, c->d_col_vecs,
+        wf_col_table(reinterpret_cast<const uint4*>(c->d_col_a), c->d_col_b, w, job.first_frame_seed, stride, o.seed_base, nf, c->d_col_vecs,
                      c->stream);
         wf_init_pool(c->pool, c->stream);
         wf_begin_job(c->d_ctl, pixels * nf, c->pool_cap, c->stream);
@@ -615,7 +614,8 @@ int trt_destroy(trt_ctx* c) {
     free_scene(c);
     cudaFree(c->d_row_a);
     cudaFree(c->d_row_b);
-    cudaFree(c->d_col_pows);
+    cudaFree(c->d_col_a);
+    cudaFree(c->d_col_b);
     cudaFree(c->d_col_vecs);
     cudaFree(c->pool_mem);
     cudaFree(c->d_compact);
@@ -924,7 +924,7 @@ int trt_trace_primary(trt_ctx* c, int w, int h, int frame_seed, const void* cam,
     JobParams job;
     fill_job(c, job, nullptr, w, h, frame_seed, 1, 1, cam, o);
     if (int rc = ensure_scratch(c, w * h)) return rc;
-    wf_col_table(c->d_col_pows, c->n_col_bits, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
+    wf_col_table(reinterpret_cast<const uint4*>(c->d_col_a), c->d_col_b, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
     wf_trace_primary(c->sc, job, frame_seed, traversal, d_id, d_t, d_ray, d_fetched, d_entered, d_tris, c->top,
                      c->scratch, c->d_ctl, launch_dims(c), c->stream);
     c->launches += 2;
@@ -976,7 +976,7 @@ int trt_rng_states(trt_ctx* c, int w, int h, int frame_seed, int seed_base, int 
     Camera dummy;
     memset(&dummy, 0, sizeof(dummy));
     fill_job(c, job, nullptr, w, h, frame_seed, 1, 1, &dummy, o);
-    wf_col_table(c->d_col_pows, c->n_col_bits, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
+    wf_col_table(reinterpret_cast<const uint4*>(c->d_col_a), c->d_col_b, w, frame_seed, 1, seed_base, 1, c->d_col_vecs, c->stream);
     wf_rng_states(job, 0, first_pixel, n, d_states, c->stream);
     c->launches += 2;
     CU(cudaStreamSynchronize(c->stream));
@@ -1212,11 +1212,14 @@ int trt_xorwow_init_host(uint64_t seed, uint64_t subsequence, uint32_t out[6]) {
 
 int trt_xorwow_rowcol_host(uint64_t seed, int w, int row, int col, uint32_t out[6]) {
     if (!out || w <= 0 || row < 0 || col < 0 || col >= w) return fail(TRT_ERR_ARG, "bad arguments");
-    uint32_t s[5], cv[5];
+    uint32_t s[5], lo_v[5], cv[5];
     xorwow_seed_state(seed, s, &out[5]);
-    Gf2Mat mc, mw, mr;
-    gf2_pow(xorwow_subsequence_matrix(), (uint64_t)col, mc);
-    gf2_matvec(mc, s, cv);
+    // column part through the two-level tables the device kernel uses: M^col = hi[col >> 6] * lo[col & 63]
+    std::vector<Gf2Mat> lo, hi;
+    xorwow_build_col_levels(w, lo, hi);
+    gf2_matvec(lo[col & 63], s, lo_v);
+    gf2_matvec(hi[col >> 6], lo_v, cv);
+    Gf2Mat mw, mr;
     gf2_pow(xorwow_subsequence_matrix(), (uint64_t)w, mw);
     gf2_pow(mw, (uint64_t)row, mr);
     gf2_matvec(mr, cv, out);

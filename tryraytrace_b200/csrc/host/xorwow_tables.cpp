@@ -121,4 +121,15 @@ void xorwow_build_col_powers(int w, std::vector<Gf2Mat>& col_pows) {
     for (int j = 1; j < bits; j++) gf2_matmul(col_pows[j - 1], col_pows[j - 1], col_pows[j]);
 }
 
+void xorwow_build_col_levels(int w, std::vector<Gf2Mat>& lo, std::vector<Gf2Mat>& hi) {
+    lo.resize(64);
+    gf2_identity(lo[0]);
+    for (int b = 1; b < 64; b++) gf2_matmul(xorwow_subsequence_matrix(), lo[b - 1], lo[b]);
+    Gf2Mat step;
+    gf2_matmul(xorwow_subsequence_matrix(), lo[63], step);  // M^64
+    hi.resize((size_t)(w + 63) / 64);
+    gf2_identity(hi[0]);
+    for (size_t a = 1; a < hi.size(); a++) gf2_matmul(step, hi[a - 1], hi[a]);
+}
+
 }  // namespace trt

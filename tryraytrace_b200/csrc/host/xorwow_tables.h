@@ -47,6 +47,10 @@ void xorwow_init_host(uint64_t seed, uint64_t subsequence, uint32_t v[5], uint32
 //   col_pows[j]   = M^(2^j)              j in [0,n_col_bits)  with 2^n_col_bits >= w
 void xorwow_build_row_matrices(int w, int h, std::vector<Gf2Mat>& row_mats);
 void xorwow_build_col_powers(int w, std::vector<Gf2Mat>& col_pows);
+// Two-level column tables: lo[b] = M^b for b in [0,64), hi[a] = M^(64a) for a in [0, ceil(w/64)); M^col =
+// hi[col >> 6] * lo[col & 63] (powers of one matrix commute), so the per-job column vectors cost two windowed
+// mat-vecs per column instead of one full mat-vec per set bit of the column index.
+void xorwow_build_col_levels(int w, std::vector<Gf2Mat>& lo, std::vector<Gf2Mat>& hi);
 
 // 4-bit window form of a matrix for the device mat-vec (kernels/xorwow.cuh): the 160 input
 // bits are cut into 40 nibbles; entry [n][v] is the XOR of the columns selected by the bits of

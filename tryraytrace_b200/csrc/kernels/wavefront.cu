@@ -148,21 +148,20 @@ __global__ void k_init_pool(PoolView pool) {
 }
 
 // ---- XORWOW column table: col_vecs[f*w + col] = M^col * v0(frame f) --------------------
-__global__ void k_col_table(const uint32_t* __restrict__ col_pows, int n_col_bits, int w, int first_frame_seed,
+// M^col = M^(64 * (col >> 6)) * M^(col & 63): two windowed mat-vecs (80 look-ups) through the two-level tables of
+// host/xorwow_tables.h, instead of one full mat-vec (160 column loads) per set bit of the column index -- the
+// kernel runs once per job in front of the first refill, 154 us -> ~20 us of a 4 ms one-frame call.
+// Table layout: entry t of `col_a` / `col_b` = window table of lo[t] for t < 64, of hi[t - 64] after that.
+__global__ void k_col_table(const uint4* __restrict__ col_a, const uint32_t* __restrict__ col_b, int w, int first_frame_seed,
                             int frame_stride, int seed_base, int n_frames, XwColVec* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)n_frames * w) return;
     const int f = (int)(i / w), col = (int)(i % w);
-    uint32_t v[5], d;
+    uint32_t v[5], t[5], d;
     xw_seed((uint32_t)(seed_base + first_frame_seed + f * frame_stride), v, &d);
-    for (int j = 0; j < n_col_bits; j++) {
-        if ((col >> j) & 1) {
-            uint32_t t[5];
-            xw_matvec(col_pows + (size_t)j * kXwMatWords, v, t);
-#pragma unroll
-            for (int k = 0; k < 5; k++) v[k] = t[k];
-        }
-    }
+    const size_t lo = (size_t)(col & 63) * kXwWindowEntries, hi = (size_t)(64 + (col >> 6)) * kXwWindowEntries;
+    xw_matvec_window(col_a + lo, col_b + lo, v, t);
+    xw_matvec_window(col_a + hi, col_b + hi, t, v);
     XwColVec e;
 #pragma unroll
     for (int k = 0; k < 5; k++) e.v[k] = v[k];
@@ -1552,11 +1551,11 @@ void wf_begin_job(Control* ctl, unsigned long long total_samples, int pool_capac
     k_begin_job<<<1, 32, 0, s>>>(ctl, total_samples, pool_capacity);
 }
 
-void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_frame_seed, int frame_stride,
+void wf_col_table(const uint4* col_a, const uint32_t* col_b, int w, int first_frame_seed, int frame_stride,
                   int seed_base, int n_frames, XwColVec* out, cudaStream_t s) {
     const long long n = (long long)n_frames * w;
-    k_col_table<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(col_pows, n_col_bits, w, first_frame_seed, frame_stride,
-                                                            seed_base, n_frames, out);
+    k_col_table<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(col_a, col_b, w, first_frame_seed, frame_stride, seed_base, n_frames,
+                                                            out);
 }
 
 // One iteration on one stream: refill -> [compact] -> trace -> shade.

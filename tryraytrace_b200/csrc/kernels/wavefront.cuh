@@ -111,7 +111,7 @@ int wf_fast_max_smem_nodes(int threads, size_t smem_limit);
 void wf_init_pool(const PoolView& pool, cudaStream_t s);
 void wf_reset_counters(Control* ctl, cudaStream_t s);
 void wf_begin_job(Control* ctl, unsigned long long total_samples, int pool_capacity, cudaStream_t s);
-void wf_col_table(const uint32_t* col_pows, int n_col_bits, int w, int first_frame_seed, int frame_stride,
+void wf_col_table(const uint4* col_a, const uint32_t* col_b, int w, int first_frame_seed, int frame_stride,
                   int seed_base, int n_frames, XwColVec* out, cudaStream_t s);
 // What the host knows when it issues an iteration (from its last completion poll; stale values are safe:
 // active_cap only shrinks and next_sample only grows within a job).
